@@ -1,0 +1,197 @@
+// chimera-b200 discrete Hankel transform: dense FP64 contraction on the tensor pipe.
+//
+// Replaces (behaviour, not code) the reference's Reikna MatrixMul calls `_ddot` /
+// `_cdot` (methods/transformer_methods_cl.py:458-480; on CPU devices literally
+// np.dot, :474-480), used by the Fourier-Bessel transforms (:296,:320,:355,:379)
+// and the spectral grad/rot operators (:111,:125,:221,:228,:248,:255).
+//
+//   C[M x N] (op)= alpha * A[M x K] . B[K x N]      A real, B real or complex
+//
+// Because A is real, a complex right-hand side is the same real GEMM on the
+// (re, im)-interleaved view with 2N columns: one kernel serves both.  FP64 does
+// not exist on tcgen05, so the tensor path for this contraction is the FP64
+// DMMA (`mma.sync.m8n8k4.f64`); operands are staged in padded shared memory
+// (conflict-free fragment reads), next k-slab prefetched into registers while the
+// current one is multiplied.  Optional fused epilogue: complex alpha and
+// accumulate-into-C, which folds the reference's zpaxz/append_c2c passes
+// (kernels/generic.cl:18-45) into the contraction.
+#include "common.cuh"
+#include "../../include/chimera_b200.h"
+
+namespace chb {
+
+constexpr int BM = 128, BN = 64, BK = 16;
+constexpr int kGemmThreads = 256;       // 8 warps: 4 (M) x 2 (N), warp tile 32 x 32
+constexpr int LDA_S = BK + 4;           // 20: (g*20 + t) mod 16 distinct over a half warp
+constexpr int LDB_S = BN + 4;           // 68: (t*68 + g) mod 16 distinct over a half warp
+
+__device__ __forceinline__ void dmma_884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+struct GemmArgs {
+  const double* __restrict__ A;
+  const double* __restrict__ B;
+  double* __restrict__ C;
+  uint32_t lda, ldb, ldc;   // in doubles
+  uint32_t M, N, K;         // N in doubles (2*Nx for complex data)
+  double alpha_re, alpha_im;
+  int complex_pairs;        // columns are (re, im) pairs -> complex alpha allowed
+  int accumulate;           // C += ... instead of C = ...
+  // optional second output of the same product: C2 (op)= alpha2 * A.B
+  double* __restrict__ C2;
+  uint32_t ldc2;
+  double alpha2_re, alpha2_im;
+  int accumulate2;
+};
+
+__device__ __forceinline__ void gemm_store(double* c, double v0, double v1, double are,
+                                           double aim, bool cplx, bool accumulate, bool pair) {
+  if (!(are == 1.0 && aim == 0.0)) {
+    if (cplx) {
+      const double re = are * v0 - aim * v1;
+      const double im = are * v1 + aim * v0;
+      v0 = re; v1 = im;
+    } else {
+      v0 *= are; v1 *= are;
+    }
+  }
+  if (pair && ((reinterpret_cast<uintptr_t>(c) & 15) == 0)) {
+    double2 o = make_double2(v0, v1);
+    if (accumulate) { double2 old = *reinterpret_cast<double2*>(c); o.x += old.x; o.y += old.y; }
+    *reinterpret_cast<double2*>(c) = o;
+  } else {
+    if (accumulate) { v0 += c[0]; if (pair) v1 += c[1]; }
+    c[0] = v0;
+    if (pair) c[1] = v1;
+  }
+}
+
+__global__ void __launch_bounds__(kGemmThreads, 2)
+dht_gemm_kernel(GemmArgs p) {
+  __shared__ double As[BM * LDA_S];
+  __shared__ double Bs[BK * LDB_S];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm = warp >> 1, wn = warp & 1;
+  const uint32_t m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+
+  // global -> register staging assignment
+  const int a_row = tid >> 1, a_k = (tid & 1) * 8;   // 8 consecutive k of one row
+  const int b_row = tid >> 4, b_col = (tid & 15) * 4; // 4 consecutive columns of one k
+  double ra[8], rb[4];
+
+  auto load_slab = [&](uint32_t k0) {
+    const uint32_t gr = m0 + a_row;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint32_t gk = k0 + a_k + i;
+      ra[i] = (gr < p.M && gk < p.K) ? __ldg(p.A + (size_t)gr * p.lda + gk) : 0.0;
+    }
+    const uint32_t gk = k0 + b_row;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t gc = n0 + b_col + i;
+      rb[i] = (gk < p.K && gc < p.N) ? __ldg(p.B + (size_t)gk * p.ldb + gc) : 0.0;
+    }
+  };
+  auto store_slab = [&]() {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) As[a_row * LDA_S + a_k + i] = ra[i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) Bs[b_row * LDB_S + b_col + i] = rb[i];
+  };
+
+  double acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  load_slab(0);
+  for (uint32_t k0 = 0; k0 < p.K; k0 += BK) {
+    __syncthreads();          // previous slab fully consumed
+    store_slab();
+    __syncthreads();
+    if (k0 + BK < p.K) load_slab(k0 + BK);   // prefetch while multiplying
+#pragma unroll
+    for (int kk = 0; kk < BK; kk += 4) {
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[(wm * 32 + i * 8 + g) * LDA_S + kk + t];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[(kk + t) * LDB_S + wn * 32 + j * 8 + g];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma_884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+  }
+
+  // epilogue: thread owns C(row g, cols 2t, 2t+1) of every 8x8 block
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t row = m0 + wm * 32 + i * 8 + g;
+    if (row >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t col = n0 + wn * 32 + j * 8 + 2 * t;
+      if (col >= p.N) continue;
+      const bool pair = (col + 1 < p.N);
+      gemm_store(p.C + (size_t)row * p.ldc + col, acc[i][j][0], acc[i][j][1], p.alpha_re,
+                 p.alpha_im, p.complex_pairs, p.accumulate, pair);
+      if (p.C2)
+        gemm_store(p.C2 + (size_t)row * p.ldc2 + col, acc[i][j][0], acc[i][j][1], p.alpha2_re,
+                   p.alpha2_im, p.complex_pairs, p.accumulate2, pair);
+    }
+  }
+}
+
+}  // namespace chb
+
+using namespace chb;
+
+static int dht_launch(const double* A, uint32_t lda, const double* B, uint32_t ldb,
+                      double* C, uint32_t ldc, uint32_t M, uint32_t K, uint32_t N,
+                      int is_complex, double alpha_re, double alpha_im, int accumulate,
+                      double* C2, uint32_t ldc2, double alpha2_re, double alpha2_im,
+                      int accumulate2, void* stream) {
+  if (M == 0 || N == 0) return CHB_OK;
+  if (!is_complex && (alpha_im != 0.0 || alpha2_im != 0.0)) return CHB_ERR_ARG;
+  GemmArgs p;
+  p.C2 = C2;
+  p.ldc2 = is_complex ? 2 * ldc2 : ldc2;
+  p.alpha2_re = alpha2_re; p.alpha2_im = alpha2_im;
+  p.accumulate2 = accumulate2;
+  p.A = A; p.B = B; p.C = C;
+  p.lda = lda;
+  p.ldb = is_complex ? 2 * ldb : ldb;
+  p.ldc = is_complex ? 2 * ldc : ldc;
+  p.M = M; p.K = K;
+  p.N = is_complex ? 2 * N : N;
+  p.alpha_re = alpha_re; p.alpha_im = alpha_im;
+  p.complex_pairs = is_complex;
+  p.accumulate = accumulate;
+  dim3 grid((p.N + BN - 1) / BN, (M + BM - 1) / BM);
+  dht_gemm_kernel<<<grid, kGemmThreads, 0, (cudaStream_t)stream>>>(p);
+  CHB_RETURN_LAST_ERROR();
+}
+
+extern "C" int chb_dht(const double* A, uint32_t lda, const double* B, uint32_t ldb,
+                       double* C, uint32_t ldc, uint32_t M, uint32_t K, uint32_t N,
+                       int is_complex, double alpha_re, double alpha_im, int accumulate,
+                       void* stream) {
+  return dht_launch(A, lda, B, ldb, C, ldc, M, K, N, is_complex, alpha_re, alpha_im,
+                    accumulate, nullptr, 0, 1.0, 0.0, 0, stream);
+}
+
+extern "C" int chb_dht2(const double* A, uint32_t lda, const double* B, uint32_t ldb,
+                        double* C1, double a1_re, double a1_im, int accumulate1, double* C2,
+                        double a2_re, double a2_im, int accumulate2, uint32_t ldc, uint32_t M,
+                        uint32_t K, uint32_t N, int is_complex, void* stream) {
+  return dht_launch(A, lda, B, ldb, C1, ldc, M, K, N, is_complex, a1_re, a1_im, accumulate1,
+                    C2, ldc, a2_re, a2_im, accumulate2, stream);
+}

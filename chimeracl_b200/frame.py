@@ -1,0 +1,49 @@
+"""Moving window + plasma injector (API of the reference's chimeraCL/frame.py)."""
+import numpy as np
+
+
+class Frame():
+    def __init__(self, configs_in, comm=None):
+        self.Args = configs_in
+        for key, default in (('Steps', 1.), ('Velocity', 0.), ('dt', 1),
+                             ('DensityProfiles', None)):
+            if key not in self.Args:
+                self.Args[key] = default
+
+    def _shift(self, steps):
+        if steps is None:
+            steps = self.Args['Steps']
+        return steps * self.Args['dt'] * self.Args['Velocity']
+
+    def shift_grids(self, grids=[], steps=None):
+        """Move Xmin/Xmax/Xgrid on host AND device (reference frame.py:22-30)."""
+        x_shift = self._shift(steps)
+        for grid in grids:
+            for store in (grid.Args, grid.DataDev):
+                for arg in ('Xmax', 'Xmin', 'Xgrid'):
+                    store[arg] += x_shift
+
+    def inject_plasma(self, species, grid, steps=None):
+        """New plasma slab at the right edge, appended, sorted and aligned
+        (reference frame.py:32-64)."""
+        x_shift = self._shift(steps)
+        for specie in species:
+            if specie.Args['Np'] == 0:
+                specie.Args['right_lim'] = grid.Args['Xmax'] - x_shift
+            left = specie.Args['right_lim']
+            domain = {'Xmin': left, 'Xmax': left + x_shift,
+                      'Rmin': grid.Args['Rmin'] * (grid.Args['Rmin'] > 0),
+                      'Rmax': grid.Args['Rmax']}
+            specie.make_new_domain(domain, density_profiles=self.Args['DensityProfiles'])
+            if 'InjectorSource' in specie.Args.keys():
+                specie.add_new_particles(specie.Args['InjectorSource'])
+            else:
+                specie.add_new_particles()
+
+        for specie in species:
+            specie.free_added()
+            specie.sort_parts(grid=grid)
+            specie.align_parts()
+            Num_ppc = np.int32(np.prod(specie.Args['Nppc']) + 1)
+            x_max = specie.DataDev['x'][-Num_ppc:].get().max()
+            specie.Args['right_lim'] = x_max + 0.5 * specie.Args['ddx']

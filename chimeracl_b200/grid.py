@@ -1,0 +1,85 @@
+"""Grid wrapper class (API of the reference's chimeraCL/grid.py)."""
+import numpy as np
+
+from .methods.generic_methods_cl import ArgsDict
+from .methods.grid_methods_cl import GridMethodsCL
+
+
+def grid_geometry(A):
+    """r-x grid geometry and index products, reference grid.py:68-103.  Pure host
+    math on a dict (no device needed)."""
+    if 'M' not in A:
+        A['M'] = 0
+    Nx, Nr = A['Nx'], A['Nr']
+    A['dx'] = (A['Xmax'] - A['Xmin']) / (Nx - 1)
+    A['dx_inv'] = 1. / A['dx']
+    A['dr'] = A['Rmax'] / (Nr - 1.5)
+    A['dr_inv'] = 1. / A['dr']
+    if 'dt' not in A:
+        A['dt'] = A['dx']
+    A['dt_inv'] = 1.0 / A['dt']
+    A['Xgrid'] = A['Xmin'] + A['dx'] * np.arange(Nx)
+    A['Rmin'] = -0.5 * A['dr']               # ghost row at r = -dr/2
+    A['Rgrid'] = A['Rmin'] + A['dr'] * np.arange(Nr)
+    A['Rmax'] = A['Rgrid'].max()
+    with np.errstate(divide='ignore'):
+        A['dV_inv'] = (A['Rgrid'] > 0) / (2 * np.pi * A['dx'] * A['dr'] * A['Rgrid'])
+    A['NxNr'] = Nr * Nx
+    A['Nxm1Nrm1'] = (Nr - 1) * (Nx - 1)
+    A['NxNrm1'] = (Nr - 1) * Nx
+    A['NxNr_4'] = Nr // 2 * Nx // 2
+    A['dont_send'] = []
+    A['dont_keep'] = []
+    return A
+
+
+class Grid(GridMethodsCL):
+    def __init__(self, configs_in, comm):
+        self.import_comm(comm)
+        self._process_configs(configs_in)
+        if 'vec_comps' not in self.Args:
+            self.Args['vec_comps'] = ['x', 'y', 'z']
+        self.init_grid_methods()
+        self.DataDev = {}
+        self._init_grid_data_on_dev()
+        self.send_args_to_dev()
+
+    def depose_charge(self, species=[]):
+        for m in range(self.Args['M'] + 1):
+            self.set_to(self.DataDev['rho_m' + str(m)], 0)
+        for parts in species:
+            self.depose_scalar(parts, 'w', 'rho', charge=parts.Args['charge'])
+        self.postproc_depose_scalar('rho')
+
+    def depose_currents(self, species=[]):
+        comps = self.Args['vec_comps']
+        for m in range(self.Args['M'] + 1):
+            for comp in comps:
+                self.set_to(self.DataDev['J' + comp + '_m' + str(m)], 0)
+        for parts in species:
+            if 'Immobile' in parts.Args.keys():
+                continue
+            self.depose_vector(parts, ['p' + comp for comp in comps], ['g_inv', 'w'], 'J',
+                               charge=parts.Args['charge'])
+        self.postproc_depose_vector('J')
+
+    def gather_and_push(self, species=[]):
+        for fld in ['E', 'B']:
+            self.preproc_project_vec(fld)
+        for parts in species:
+            if 'Immobile' in parts.Args.keys():
+                continue
+            self._gather_and_push(parts, ['E', 'B'])
+
+    def _process_configs(self, configs_in):
+        self.Args = grid_geometry(ArgsDict(configs_in))
+
+    def _init_grid_data_on_dev(self):
+        names = [f + comp for f in ('E', 'B', 'J', 'G') for comp in self.Args['vec_comps']]
+        names.append('rho')
+        shape = (self.Args['Nr'], self.Args['Nx'])
+        for name in names:
+            self.DataDev[name + '_m0'] = self.dev_arr(val=0, dtype=np.double, shape=shape)
+            for m in range(1, self.Args['M'] + 1):
+                self.DataDev[name + '_m' + str(m)] = self.dev_arr(val=0, dtype=np.complex128,
+                                                                 shape=shape)

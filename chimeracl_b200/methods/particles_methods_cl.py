@@ -1,0 +1,298 @@
+"""Particle methods mixin: coordinate push, cell sort, align, particle creation.
+
+Interface of the reference's chimeraCL/methods/particles_methods_cl.py (same method
+names / DataDev keys); compute goes to libchimera_b200.so:
+
+  push_coords     :206-223 -> chb_push_xyz
+  index_sort      :225-261 -> chb_index_and_sum (or fused chb_push_index),
+                              chb_cell_offsets, chb_sort_scatter_stable
+  align_and_damp  :263-286 -> chb_align (all attributes in one launch)
+
+Particle creation (make_new_domain / make_new_beam / dens_profile, :66-204) is the
+init path: same lattice / profile formulas evaluated with torch ops on the device.
+"""
+import numpy as np
+import torch
+
+from .. import _lib
+from ..devarray import DevArray, sqrt  # noqa: F401  (sqrt re-exported like the reference)
+from .generic_methods_cl import GenericMethodsCL
+
+
+class ParticleMethodsCL(GenericMethodsCL):
+
+    def init_particle_methods(self):
+        self.init_generic_methods()
+        self._ws = {}           # persistent sort workspaces (replace the MemoryPools)
+        self._pending_push = None
+
+    # ------------------------------------------------------------------ buffers
+    def _buf(self, name, n, dtype):
+        """Persistent, grow-only device buffer; returns a DevArray view of n items."""
+        cur = self._ws.get(name)
+        if cur is None or cur.size < n or cur.dtype != np.dtype(dtype):
+            cap = max(int(n * 1.1) + 16, 16)
+            cur = DevArray.empty(cap, dtype, self.comm.device)
+            self._ws[name] = cur
+        return cur[:n]
+
+    def _attr_names(self):
+        if 'Immobile' in self.Args.keys():
+            return ['x', 'y', 'z', 'w']
+        return ['x', 'y', 'z', 'px', 'py', 'pz', 'w', 'g_inv']
+
+    # ------------------------------------------------------------------ creation
+    def add_new_particles(self, source=None):
+        DataSrc = self.DataDev if source is None else source.DataDev
+        for arg in self._attr_names():
+            self.DataDev[arg] = DevArray(torch.cat((self.DataDev[arg].t,
+                                                    DataSrc[arg + '_new'].t)))
+        self.reset_num_parts()
+        self.flag_sorted = False
+
+    def make_new_domain(self, parts_in, density_profiles=None):
+        dev = self.comm.device
+        xmin, xmax, rmin, rmax = [parts_in[k] for k in ('Xmin', 'Xmax', 'Rmin', 'Rmax')]
+        dx, dr = self.Args['dx'], self.Args['dr']
+        Nx_loc = int(np.ceil((xmax - xmin) / dx) + 1)
+        Nr_loc = int(np.round((rmax - rmin) / dr) + 1)
+        Xgrid = xmin + dx * np.arange(Nx_loc)
+        Rgrid = rmin + dr * np.arange(Nr_loc)
+        self.Args['right_lim'] = Xgrid[-1]
+
+        npx, npr, npt = (int(v) for v in self.Args['Nppc'])
+        ncx, ncr = Nx_loc - 1, Nr_loc - 1
+        ncells = ncx * ncr
+        theta_var = torch.rand(ncells, dtype=torch.float64, device=dev,
+                               generator=self.comm.generator) * (2 * np.pi)
+        self._fill_grid(theta_var, Xgrid, Rgrid, (npx, npr, npt))
+        self.DataDev['w_new'] *= self.Args['w0']
+
+        if density_profiles is not None:
+            for profile in density_profiles:
+                if profile['coord'] != 'x':
+                    print('Only longitudinal profiling is implemented')
+                    continue
+                self.dens_profile(profile['points'], profile['values'],
+                                  parts_in['Xmin'], parts_in['Xmax'],
+                                  coord='x_new', weight='w_new')
+
+        if 'Immobile' in self.Args.keys():
+            return
+        Np = ncells * npx * npr * npt
+        for arg in ('px', 'py', 'pz'):
+            centre = parts_in.setdefault(arg + '_c', 0)
+            spread = parts_in.setdefault('d' + arg, 0)
+            buf = DevArray.empty(Np, np.double, dev)
+            if spread != 0:
+                self._fill_arr_randn(buf, mu=centre, sigma=spread)
+            else:
+                buf.fill(centre)
+            self.DataDev[arg + '_new'] = buf
+        self._set_g_inv_new()
+
+    def _fill_grid(self, theta_var, Xgrid, Rgrid, nppc):
+        """Regular (x, r, theta) lattice in every cell with a per-cell theta offset:
+        the layout of fill_grid, reference kernels/particles_generic.cl:33-84
+        (particle order inside a cell: theta slowest, then r, then x)."""
+        dev = self.comm.device
+        npx, npr, npt = nppc
+        ncx = Xgrid.size - 1
+        xg = torch.from_numpy(Xgrid).to(dev)
+        rg = torch.from_numpy(Rgrid).to(dev)
+        ncells = ncx * (Rgrid.size - 1)
+        ic = torch.arange(ncells, device=dev)
+        ir = torch.div(ic, ncx, rounding_mode='floor')
+        ix = ic - ncx * ir
+        x_lo, r_lo = xg[ix], rg[ir]
+        Lx, Lr = xg[ix + 1] - x_lo, rg[ir + 1] - r_lo
+        fx = (0.5 + torch.arange(npx, device=dev, dtype=torch.float64)) * (1. / npx)
+        fr = (0.5 + torch.arange(npr, device=dev, dtype=torch.float64)) * (1. / npr)
+        th = theta_var[:, None] + torch.arange(npt, device=dev, dtype=torch.float64)[None, :] \
+            * (2 * np.pi / npt)
+        shape = (ncells, npt, npr, npx)
+        rp = (r_lo[:, None] + fr[None, :] * Lr[:, None])[:, None, :, None].expand(shape)
+        xp = (x_lo[:, None] + fx[None, :] * Lx[:, None])[:, None, None, :].expand(shape)
+        sin_t = torch.sin(th)[:, :, None, None].expand(shape)
+        cos_t = torch.cos(th)[:, :, None, None].expand(shape)
+        self.DataDev['x_new'] = DevArray(xp.reshape(-1).contiguous())
+        self.DataDev['y_new'] = DevArray((rp * sin_t).reshape(-1).contiguous())
+        self.DataDev['z_new'] = DevArray((rp * cos_t).reshape(-1).contiguous())
+        self.DataDev['w_new'] = DevArray(rp.reshape(-1).contiguous())
+
+    def _set_g_inv_new(self):
+        D = self.DataDev
+        D['g_inv_new'] = DevArray(torch.rsqrt(1 + D['px_new'].t ** 2 + D['py_new'].t ** 2
+                                              + D['pz_new'].t ** 2))
+
+    def make_new_beam(self, parts_in):
+        dev = self.comm.device
+        Np = int(parts_in['Np'])
+        for arg in ('x', 'y', 'z'):
+            buf = DevArray.empty(Np, np.double, dev)
+            self._fill_arr_randn(buf, mu=parts_in[arg + '_c'], sigma=parts_in['L' + arg])
+            self.DataDev[arg + '_new'] = buf
+        for arg in ('px', 'py', 'pz'):
+            buf = DevArray.empty(Np, np.double, dev)
+            self._fill_arr_randn(buf, mu=parts_in.setdefault(arg + '_c', 0),
+                                 sigma=parts_in.setdefault('d' + arg, 0))
+            self.DataDev[arg + '_new'] = buf
+        w = DevArray.empty(Np, np.double, dev)
+        w.fill(parts_in['FullCharge'] / parts_in['Np'])
+        self.DataDev['w_new'] = w
+        self._set_g_inv_new()
+
+    def dens_profile(self, x_prf, f_prf, xmin, xmax, coord='x', weight='w'):
+        """Piecewise-linear density profile (reference :179-204 and
+        kernels/particles_generic.cl:6-30)."""
+        x_prf = np.array(x_prf, dtype=np.double)
+        f_prf = np.array(f_prf, dtype=np.double)
+        i_start = (x_prf < xmin).sum() - 1
+        i_stop = (x_prf < xmax).sum() + 1
+        dev = self.comm.device
+        x_loc = torch.from_numpy(x_prf[i_start:i_stop]).to(dev)
+        f_loc = torch.from_numpy(f_prf[i_start:i_stop]).to(dev)
+        dxm1 = 1. / (x_loc[1:] - x_loc[:-1])
+        x = self.DataDev[coord].t
+        # interval ix with x_loc[ix] < x <= x_loc[ix+1]
+        ix = torch.searchsorted(x_loc, x, right=False) - 1
+        ix = ix.clamp_(0, x_loc.numel() - 2)
+        f_minus = f_loc[ix] * dxm1[ix]
+        f_plus = f_loc[ix + 1] * dxm1[ix]
+        self.DataDev[weight].t.mul_(f_minus * (x_loc[ix + 1] - x) + f_plus * (x - x_loc[ix]))
+
+    # ------------------------------------------------------------------ hot path
+    def push_coords(self, mode='half'):
+        if self.Args['Np'] == 0:
+            return
+        if 'Immobile' in self.Args.keys():
+            return
+        which_dt = 'dt_2' if mode == 'half' else 'dt'
+        D = self.DataDev
+        if getattr(self, 'fuse_push_sort', False):
+            # executed together with the cell indexing in the next sort_parts()
+            # (one pass over the particles, chb_push_index); flushed by anything
+            # else that looks at the coordinates
+            self._flush_pending_push()
+            self._pending_push = which_dt
+        else:
+            self._call('chb_push_xyz', D['x'].ptr, D['y'].ptr, D['z'].ptr, D['px'].ptr,
+                       D['py'].ptr, D['pz'].ptr, D['g_inv'].ptr, D[which_dt].ptr,
+                       int(self.Args['Np']))
+        self.flag_sorted = False
+
+    def _flush_pending_push(self):
+        which_dt = self._pending_push
+        if which_dt is None:
+            return
+        self._pending_push = None
+        D = self.DataDev
+        self._call('chb_push_xyz', D['x'].ptr, D['y'].ptr, D['z'].ptr, D['px'].ptr,
+                   D['py'].ptr, D['pz'].ptr, D['g_inv'].ptr, D[which_dt].ptr,
+                   int(self.Args['Np']))
+
+    def index_sort(self, grid):
+        lib, st = self._lib, self._stream
+        D, G = self.DataDev, grid.DataDev
+        Np = int(self.Args['Np'])
+        nbins = int(grid.Args['Nxm1Nrm1']) + 1
+        Nx, Nr = int(grid.Args['Nx']), int(grid.Args['Nr'])
+
+        D['indx_in_cell'] = self._buf('indx_in_cell', Np, np.uint32)
+        D['sum_in_cell'] = self._buf('sum_in_cell', nbins, np.uint32)
+        D['cell_offset'] = self._buf('cell_offset', nbins + 1, np.uint32)
+        D['sort_indx'] = self._buf('sort_indx', Np, np.uint32)
+        cursor = self._buf('cursor', nbins, np.uint32)
+        if 'Np_stay_dev' not in D:
+            D['Np_stay_dev'] = DevArray.zeros(1, np.uint32, self.comm.device)
+            self._np_stay_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        D['sum_in_cell'].t.zero_()
+
+        geom = (G['Xmin'].ptr, G['dx_inv'].ptr, G['Rmin'].ptr, G['dr_inv'].ptr)
+        which_dt, self._pending_push = self._pending_push, None
+        if which_dt is not None:
+            _lib.check(lib.chb_push_index(
+                D['x'].ptr, D['y'].ptr, D['z'].ptr, D['px'].ptr, D['py'].ptr, D['pz'].ptr,
+                D['g_inv'].ptr, D[which_dt].ptr, D['indx_in_cell'].ptr, D['sum_in_cell'].ptr,
+                Np, Nx, Nr, *geom, st), 'chb_push_index')
+        else:
+            _lib.check(lib.chb_index_and_sum(
+                D['x'].ptr, D['y'].ptr, D['z'].ptr, D['indx_in_cell'].ptr,
+                D['sum_in_cell'].ptr, Np, Nx, Nr, *geom, st), 'chb_index_and_sum')
+
+        ws_bytes = lib.chb_cell_offsets_workspace_bytes(nbins)
+        ws = self._buf('scan_ws', (ws_bytes + 3) // 4, np.uint32)
+        _lib.check(lib.chb_cell_offsets(D['sum_in_cell'].ptr, nbins, D['cell_offset'].ptr,
+                                        cursor.ptr, D['Np_stay_dev'].ptr, ws.ptr, ws_bytes, st),
+                   'chb_cell_offsets')
+
+        # Np_stay = cell_offset[-2]: asynchronous read-back, waited for on demand
+        host = self._np_stay_host
+        host.copy_(D['Np_stay_dev'].t, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+
+        def _resolve():
+            ev.synchronize()
+            return int(host.item())
+        self.Args.set_lazy('Np_stay', _resolve)
+
+        sb = lib.chb_sort_workspace_bytes(Np, nbins)
+        sws = self._buf('sort_ws', (sb + 3) // 4, np.uint32)
+        _lib.check(lib.chb_sort_scatter_stable(D['indx_in_cell'].ptr, D['cell_offset'].ptr,
+                                               cursor.ptr, D['sort_indx'].ptr, Np, nbins,
+                                               sws.ptr, sb, st), 'chb_sort_scatter_stable')
+
+    def align_and_damp(self, comps_align):
+        Np_stay = int(self.Args['Np_stay'])
+        dev = self.comm.device
+        if Np_stay == 0:
+            for comp in comps_align + ['sort_indx', ]:
+                self.DataDev[comp] = DevArray.empty(0, self.DataDev[comp].dtype, dev)
+            self.reset_num_parts()
+            return
+        new = [DevArray.empty(Np_stay, np.double, dev) for _ in comps_align]
+        src = _lib.ptr_array([self.DataDev[c].ptr for c in comps_align])
+        dst = _lib.ptr_array([a.ptr for a in new])
+        sort_new = DevArray.empty(Np_stay, np.uint32, dev)
+        self._call('chb_align', src, dst, len(comps_align), self.DataDev['sort_indx'].ptr,
+                   Np_stay, sort_new.ptr)
+        for comp, arr in zip(comps_align, new):
+            self.DataDev[comp] = arr
+        self.DataDev['sort_indx'] = sort_new
+        self.reset_num_parts()
+
+    def reset_num_parts(self, Np=None):
+        if Np is None:
+            Np = self.DataDev['x'].size
+        self.DataDev['Np'].fill(Np)
+        self.Args['Np'] = Np
+        self.Args['Np_stay'] = Np
+        if 'Np_stay_dev' in self.DataDev:
+            self.DataDev['Np_stay_dev'].fill(Np)
+
+    # ------------------------------------------------------------------ misc
+    def _fill_arr_randn(self, arr, mu=0, sigma=1):
+        arr.t.normal_(mean=float(mu), std=float(sigma), generator=self.comm.generator) \
+            if sigma != 0 else arr.t.fill_(float(mu))
+
+    def _fill_arr_rand(self, arr, xmin=0, xmax=1):
+        arr.t.uniform_(float(xmin), float(xmax), generator=self.comm.generator)
+
+    def _cumsum(self, arr_in, allocator=None, output_dtype=np.uint32):
+        """[0, inclusive_scan(arr_in)] (reference :303-311) via chb_cell_offsets."""
+        lib, n = self._lib, arr_in.size
+        out = DevArray.empty(n + 1, np.uint32, self.comm.device)
+        ws_bytes = lib.chb_cell_offsets_workspace_bytes(n)
+        ws = self._buf('scan_ws', (ws_bytes + 3) // 4, np.uint32)
+        _lib.check(lib.chb_cell_offsets(arr_in.ptr, n, out.ptr, None, None, ws.ptr,
+                                        ws_bytes, self._stream), 'chb_cell_offsets')
+        return out
+
+    def free_mp(self):
+        # sort temporaries live in persistent workspaces; nothing to release
+        pass
+
+    def free_added(self):
+        for arg in self._attr_names():
+            self.DataDev[arg + '_new'] = None

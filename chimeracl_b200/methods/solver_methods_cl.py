@@ -1,0 +1,55 @@
+"""Maxwell (PSATD) solver methods mixin -- interface of the reference's
+chimeraCL/methods/solver_methods_cl.py.
+
+  advance_fields (:43-62) -> chb_psatd_advance, one launch per azimuthal mode
+  profile_edges  (:64-83) -> chb_profile_edges, all components/modes in one launch
+                             touching only the 2*DampCells edge columns per side
+"""
+import numpy as np
+
+from .. import _lib
+from .generic_methods_cl import GenericMethodsCL
+
+
+def damping_profile(N):
+    """sin^2 absorbing-edge profile over 2N cells (reference :32-41)."""
+    N = int(N)
+    z = np.arange(2 * N)
+    z_shft = 3. * (z - N + 1) / (N + 1)
+    return ((z < 4. * N / 3) * (z >= N) * np.sin(0.5 * np.pi * z_shft) ** 2
+            + (z >= 4. * N / 3)).astype(np.double)
+
+
+class SolverMethodsCL(GenericMethodsCL):
+    def init_solver_methods(self):
+        self.init_generic_methods()
+        if 'DampCells' in self.Args:
+            self._init_field_damping()
+
+    def _init_field_damping(self):
+        self.Args['DampProfile'] = damping_profile(self.Args['DampCells'])
+        self.Args['dont_keep'].append('DampProfile')
+        self.Args['dont_send'].append('DampCells')
+
+    def advance_fields(self, vecs):
+        D = self.DataDev
+        comps = self.Args['vec_comps']
+        for m in range(self.Args['M'] + 1):
+            ms = '_m' + str(m)
+            groups = [_lib.ptr_array([D[v + c + '_fb' + ms].ptr for c in comps]) for v in vecs]
+            self._call('chb_psatd_advance', int(self.Args['NxNrm1']), D['dt_inv'].ptr,
+                       D['MxSlv_cos(wdt)' + ms].ptr, D['MxSlv_sin(wdt)*w' + ms].ptr,
+                       D['MxSlv_1/w**2' + ms].ptr, *groups)
+
+    def profile_edges(self, flds):
+        arrays = []
+        for fld in flds:
+            for comp in self.Args['vec_comps']:
+                for m in range(self.Args['M'] + 1):
+                    arrays.append(self.DataDev[fld + comp + '_m' + str(m)])
+        for i in range(0, len(arrays), 16):
+            chunk = arrays[i:i + 16]
+            self._call('chb_profile_edges', _lib.ptr_array([a.ptr for a in chunk]),
+                       _lib.int_array([1 if a.dtype == np.complex128 else 0 for a in chunk]),
+                       len(chunk), self.DataDev['DampProfile'].ptr, int(self.Args['Nr']),
+                       int(self.Args['Nx']), 2 * int(self.Args['DampCells']))

@@ -1,0 +1,254 @@
+"""Fourier-Bessel transformer methods mixin.
+
+Interface of the reference's chimeraCL/methods/transformer_methods_cl.py (same
+method names, DataDev keys and argument meaning).  Differences are only in how the
+work is scheduled on the device:
+
+  transform_field (:38-64) / _transform_forward (:290-332) / _transform_backward
+  (:334-383) / _half_transform_* (:385-455):
+      DHT  = chb_dht  (FP64 DMMA contraction reading / writing rows [1:] in place)
+      FFT  = chb_fft_x (in-smem FFT with the cast, phase shift and real-part
+             extraction fused into its load / store) -- 2 launches per
+             component-mode instead of 5-6 full-array passes.
+  field_grad (:87-133), field_rot (:185-263): same operator algebra, with the
+      "b = dDHT.x; y += a*b; z += c*b" triples folded into one two-output
+      contraction (chb_dht2).
+"""
+import numpy as np
+
+from .. import _lib
+from ..devarray import DevArray
+from .generic_methods_cl import GenericMethodsCL
+
+
+def _next_pow2(n):
+    p = 1
+    while p < n:
+        p <<= 1
+    return p
+
+
+def fft_plan_tables(Nx):
+    """Host-side plan for chb_fft_x: (L, twiddles[L], chirp[Nx] | None, bfft[L] | None).
+    Power-of-two Nx -> direct; otherwise Bluestein with L = pow2 >= 2Nx-1."""
+    pow2 = Nx >= 8 and (Nx & (Nx - 1)) == 0
+    L = Nx if pow2 else max(_next_pow2(2 * Nx - 1), 8)
+    j = np.arange(L)
+    tw = np.exp(-2j * np.pi * j / L)
+    if pow2:
+        return L, tw, None, None
+    n = np.arange(Nx, dtype=np.int64)
+    # exp(-i pi n^2 / Nx) with the exponent reduced mod 2Nx for accuracy
+    chirp = np.exp(-1j * np.pi * ((n * n) % (2 * Nx)) / Nx)
+    b = np.zeros(L, dtype=np.complex128)
+    b[:Nx] = np.conj(chirp)
+    b[L - Nx + 1:] = np.conj(chirp[1:][::-1])
+    bfft = np.fft.fft(b) / L
+    return L, tw, chirp, bfft
+
+
+class TransformerMethodsCL(GenericMethodsCL):
+    def init_transformer_methods(self):
+        self.init_generic_methods()
+        self._prepare_fft()
+        self._prepare_dot()
+
+    # ------------------------------------------------------------------ plans
+    def _prepare_fft(self):
+        Nx = int(self.Args['Nx'])
+        L, tw, chirp, bfft = fft_plan_tables(Nx)
+        if L > self._lib.chb_fft_max_pow2():
+            raise ValueError("chimera_b200: Nx=%d needs an FFT of length %d > %d "
+                             "(multi-pass FFT not implemented yet)" %
+                             (Nx, L, self._lib.chb_fft_max_pow2()))
+        dev = self.comm.device
+        self._fft_L = L
+        self._fft_tw = DevArray.from_numpy(tw, dev)
+        self._fft_chirp = DevArray.from_numpy(chirp, dev) if chirp is not None else None
+        self._fft_bfft = DevArray.from_numpy(bfft, dev) if bfft is not None else None
+
+    def _fft_rows(self, src, dst, direction, phase=None, in_real=False, out_real=False):
+        """dst = FFT_x(src) row by row; src/dst are 2-D DevArrays (views allowed)."""
+        rows, Nx = src.shape
+        self._call('chb_fft_x', src.ptr, dst.ptr, rows, Nx, src.t.stride(0), dst.t.stride(0),
+                   1 if direction == 1 else 0, int(in_real), int(out_real),
+                   phase.ptr if phase is not None else None,
+                   1 if direction == 1 else 0, self._fft_tw.ptr, self._fft_L,
+                   self._fft_chirp.ptr if self._fft_chirp is not None else None,
+                   self._fft_bfft.ptr if self._fft_bfft is not None else None)
+
+    def _fft(self, arr_out, arr, dir):
+        """Plain FFT along axis 1 (numpy conventions, normalised inverse): the
+        reference's Reikna plan call `_fft(out, in, inverse)` (:507-509)."""
+        self._fft_rows(arr, arr_out, dir)
+        return arr_out
+
+    def _prepare_dot(self):
+        pass
+
+    def _dot(self, c, a, b, alpha=1.0, accumulate=False):
+        cplx = b.dtype == np.complex128
+        M, K = a.shape
+        N = b.shape[1]
+        alpha = complex(alpha)
+        self._call('chb_dht', a.ptr, a.t.stride(0), b.ptr, b.t.stride(0), c.ptr, c.t.stride(0),
+                   M, K, N, int(cplx), alpha.real, alpha.imag, int(accumulate))
+
+    def _ddot(self, c, a, b):
+        self._dot(c, a, b)
+
+    def _cdot(self, c, a, b):
+        self._dot(c, a, b)
+
+    def _cdot2(self, a, b, c1, alpha1, acc1, c2, alpha2, acc2):
+        M, K = a.shape
+        N = b.shape[1]
+        a1, a2 = complex(alpha1), complex(alpha2)
+        self._call('chb_dht2', a.ptr, a.t.stride(0), b.ptr, b.t.stride(0), c1.ptr, a1.real,
+                   a1.imag, int(acc1), c2.ptr, a2.real, a2.imag, int(acc2), c1.t.stride(0),
+                   M, K, N, 1)
+
+    # ------------------------------------------------------------------ transforms
+    def transform_field(self, arg_cmp, dir, mode):
+        D = self.DataDev
+        # phase from the HOST Xmin (moving-window aware), reference :40-44
+        self._call('chb_get_phase', D['phs_shft'].ptr, D['kx'].ptr, float(self.Args['Xmin']),
+                   int(dir), int(self.Args['Nx']))
+        if dir == 0:
+            op = self._transform_forward if mode == 'full' else self._half_transform_forward
+            op('DHT_m', arg_cmp + '_m', arg_cmp + '_fb_m', D['phs_shft'])
+        elif dir == 1:
+            op = self._transform_backward if mode == 'full' else self._half_transform_backward
+            op('DHT_inv_m', arg_cmp + '_fb_m', arg_cmp + '_m', D['phs_shft'])
+
+    def _transform_forward(self, dht_arg, arg_in, arg_out, phs_shft):
+        D = self.DataDev
+        for m in range(self.Args['M'] + 1):
+            src = D[arg_in + str(m)][1:]
+            if m == 0:
+                self._dot(D['fld_buff1_d'], D[dht_arg + '0'], src)
+                self._fft_rows(D['fld_buff1_d'], D[arg_out + '0'], 0, phs_shft, in_real=True)
+            else:
+                self._dot(D['fld_buff0_c'], D[dht_arg + str(m)], src)
+                self._fft_rows(D['fld_buff0_c'], D[arg_out + str(m)], 0, phs_shft)
+
+    def _transform_backward(self, dht_arg, arg_in, arg_out, phs_shft):
+        D = self.DataDev
+        for m in range(self.Args['M'] + 1):
+            dst = D[arg_out + str(m)][1:]
+            if m == 0:
+                self._fft_rows(D[arg_in + '0'], D['fld_buff0_d'], 1, phs_shft, out_real=True)
+                self._dot(dst, D[dht_arg + '0'], D['fld_buff0_d'])
+            else:
+                self._fft_rows(D[arg_in + str(m)], D['fld_buff0_c'], 1, phs_shft)
+                self._dot(dst, D[dht_arg + str(m)], D['fld_buff0_c'])
+
+    def _half_transform_backward(self, dht_arg, arg_in, arg_out, phs_shft):
+        D = self.DataDev
+        for m in range(self.Args['M'] + 1):
+            self._fft_rows(D[arg_in + str(m)], D[arg_out + str(m)][1:], 1, phs_shft,
+                           out_real=(m == 0))
+
+    def _half_transform_forward(self, dht_arg, arg_in, arg_out, phs_shft):
+        D = self.DataDev
+        for m in range(self.Args['M'] + 1):
+            self._fft_rows(D[arg_in + str(m)][1:], D[arg_out + str(m)], 0, phs_shft,
+                           in_real=(m == 0))
+
+    # ------------------------------------------------------------------ spectral operators
+    def field_poiss_vec(self, fld):
+        for m in range(self.Args['M'] + 1):
+            for comp in self.Args['vec_comps']:
+                self.mult_elementwise(self.DataDev['Poiss_m' + str(m)],
+                                      self.DataDev[fld + comp + '_fb_m' + str(m)])
+
+    def field_poiss_scl(self, fld):
+        for m in range(self.Args['M'] + 1):
+            self.mult_elementwise(self.DataDev['Poiss_m' + str(m)],
+                                  self.DataDev[fld + '_fb_m' + str(m)])
+
+    def fields_smooth(self, flds):
+        for m in range(self.Args['M'] + 1):
+            for fld in flds:
+                self.mult_elementwise(self.DataDev['SmoothingFilter_m' + str(m)],
+                                      self.DataDev[fld + '_fb_m' + str(m)])
+
+    def field_grad(self, scl_in, vec_out):
+        D, M = self.DataDev, self.Args['M']
+        self._get_mm1_scl(scl_in)
+        for m in range(M + 1):
+            ox, oy, oz = (D[vec_out + c + '_fb_m' + str(m)] for c in 'xyz')
+            self.ab_dot_x(1.j, D['kx'], D[scl_in + '_fb_m' + str(m)], ox)
+            if m > 0:
+                src = D[scl_in + '_fb_m' + str(m - 1)]
+            elif M > 0:
+                src = D['buff_fb_m-1_x']
+            else:
+                self.set_to(oy, 0.)
+                self.set_to(oz, 0.)
+                continue
+            # oy = -b, oz = -i b with b = dDHT_minus . src
+            self._cdot2(D['dDHT_minus_m' + str(m)], src, oy, -1., False, oz, -1.j, False)
+            if m < M:
+                # oy += b, oz -= i b with b = dDHT_plus . scl_{m+1}
+                self._cdot2(D['dDHT_plus_m' + str(m)], D[scl_in + '_fb_m' + str(m + 1)],
+                            oy, 1., True, oz, -1.j, True)
+
+    def field_div(self, vec_in, scl_out):
+        D, M = self.DataDev, self.Args['M']
+        for comp in ['y', 'z']:
+            self._get_mm1_scl(vec_in + comp, comp)
+        for m in range(M + 1):
+            out = D[scl_out + '_fb_m' + str(m)]
+            self.ab_dot_x(1.j, D['kx'], D[vec_in + 'x' + '_fb_m' + str(m)], out)
+            if m > 0:
+                fy, fz = (D[vec_in + c + '_fb_m' + str(m - 1)] for c in 'yz')
+            elif M > 0:
+                fy, fz = D['buff_fb_m-1_y'], D['buff_fb_m-1_z']
+            else:
+                continue
+            self.axpbyz(-1.j, fz, -1.0, fy, D['fld_buff0_c'])
+            self._dot(out, D['dDHT_minus_m' + str(m)], D['fld_buff0_c'], accumulate=True)
+            if m < M:
+                fy, fz = (D[vec_in + c + '_fb_m' + str(m + 1)] for c in 'yz')
+                self.axpbyz(-1.j, fz, 1.0, fy, D['fld_buff0_c'])
+                self._dot(out, D['dDHT_plus_m' + str(m)], D['fld_buff0_c'], accumulate=True)
+
+    def field_rot(self, fld_in, fld_out):
+        D, M = self.DataDev, self.Args['M']
+        self._get_mm1_vec(fld_in)
+        for m in range(M + 1):
+            ox, oy, oz = (D[fld_out + c + '_fb_m' + str(m)] for c in 'xyz')
+            self.ab_dot_x(-1.j, D['kx'], D[fld_in + 'z' + '_fb_m' + str(m)], oy)
+            self.ab_dot_x(1.j, D['kx'], D[fld_in + 'y' + '_fb_m' + str(m)], oz)
+            if m > 0:
+                fx, fy, fz = (D[fld_in + c + '_fb_m' + str(m - 1)] for c in 'xyz')
+            elif M > 0:
+                fx, fy, fz = (D['buff_fb_m-1_' + c] for c in 'xyz')
+            else:
+                self.set_to(ox, 0.0)
+                continue
+            dm = D['dDHT_minus_m' + str(m)]
+            self.axpbyz(-1, fz, 1.j, fy, D['fld_buff0_c'])
+            self._dot(ox, dm, D['fld_buff0_c'])                       # ox  = dDHT-.(-fz + i fy)
+            self._cdot2(dm, fx, oy, -1.j, True, oz, 1., True)         # oy -= i b, oz += b
+            if m < M:
+                fx, fy, fz = (D[fld_in + c + '_fb_m' + str(m + 1)] for c in 'xyz')
+                dp = D['dDHT_plus_m' + str(m)]
+                self.axpbyz(1, fz, 1.j, fy, D['fld_buff0_c'])
+                self._dot(ox, dp, D['fld_buff0_c'], accumulate=True)  # ox += dDHT+.(fz + i fy)
+                self._cdot2(dp, fx, oy, -1.j, True, oz, -1., True)    # oy -= i b, oz -= b
+
+    def _get_mm1_vec(self, fld):
+        if self.Args['M'] == 0:
+            return
+        for comp in self.Args['vec_comps']:
+            self._get_mm1_scl(fld + comp, comp)
+
+    def _get_mm1_scl(self, fld, comp='x'):
+        # for a scalar the X component of the buffer is used (reference :277-288)
+        if self.Args['M'] == 0:
+            return
+        self._call('chb_get_m1', self.DataDev['buff_fb_m-1_' + comp].ptr,
+                   self.DataDev[fld + '_fb_m1'].ptr, int(self.Args['NxNrm1']),
+                   int(self.Args['Nx']))

@@ -1,0 +1,53 @@
+"""Multi-GPU plumbing: one process per GPU (torchrun), particles sharded over ranks,
+every rank holds the full grid; the only exchange step of the hot path is the sum
+of the raw rho / J deposits over ranks (NCCL all-reduce over NVLink), issued before
+the axis / volume post-processing.  The same code runs on gloo/CPU tensors for the
+world_size-2 tests."""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_distributed(comm=None, backend=None):
+    """Initialise torch.distributed from the torchrun environment (no-op for a
+    single process) and attach the process group to the Communicator."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return None
+    if not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        kw = {}
+        if backend == "nccl" and comm is not None:
+            kw["device_id"] = comm.device
+        dist.init_process_group(backend=backend, **kw)
+    pg = dist.group.WORLD
+    if comm is not None:
+        comm.process_group = pg
+    return pg
+
+
+def shard_range(n, rank, world):
+    """Contiguous-by-index split of n particles: [lo, hi) of this rank."""
+    base, rem = divmod(int(n), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def allreduce_sum(tensors, group=None):
+    """In-place sum over ranks of a list of (real or complex) tensors.  The arrays
+    are packed into one flat FP64 buffer so that the exchange is a single
+    collective per deposit (payload: SURVEY.md section 8e)."""
+    if group is None and not dist.is_initialized():
+        return
+    if dist.get_world_size(group) == 1:
+        return
+    views = [torch.view_as_real(t).reshape(-1) if t.is_complex() else t.reshape(-1)
+             for t in tensors]
+    flat = torch.cat(views)
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    off = 0
+    for v in views:
+        v.copy_(flat[off:off + v.numel()])
+        off += v.numel()

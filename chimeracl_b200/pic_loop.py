@@ -1,0 +1,134 @@
+"""PIC time-step driver (API of the reference's chimeraCL/pic_loop.py).
+
+The step sequence is the reference's (pic_loop.py:57-142); every phase only enqueues
+work on the rank's CUDA stream -- there is no host synchronisation inside a step.
+With timit=True the phases are bracketed by CUDA events and accumulated (in seconds)
+under the reference's Timer keys."""
+import numpy as np
+import torch
+
+loop_steps = ['frame', 'push-x', 'sort', 'depose',
+              'transform', 'smooth', 'data_copy',
+              'grad', 'push-eb', 'damp-eb', 'restore_B',
+              'gather + push-p']
+
+
+class PIC_loop:
+    def __init__(self, solvers=[], species=[], frames=[], diags=[], timit=False,
+                 fuse_push_sort=True):
+        self.solvers = solvers
+        self.mainsolver = self.solvers[0]
+        self.species = species
+        self.frames = frames
+        self.diags = diags
+        self.timit = timit
+        self.it = 0
+        for parts in self.species:
+            parts.fuse_push_sort = bool(fuse_push_sort)
+        if self.timit is True:
+            self.Timer = {key: 0 for key in loop_steps}
+            self._events = []
+
+    # ---- phase timer (CUDA events; resolved lazily by timer_collect)
+    def timer_start(self):
+        if self.timit is True:
+            self._t0 = torch.cuda.Event(enable_timing=True)
+            self._t0.record()
+
+    def timer_record(self, method_str):
+        if self.timit is True:
+            t1 = torch.cuda.Event(enable_timing=True)
+            t1.record()
+            self._events.append((method_str, self._t0, t1))
+
+    def timer_collect(self):
+        if self.timit is not True:
+            return {}
+        torch.cuda.synchronize()
+        for key, t0, t1 in self._events:
+            self.Timer[key] += t0.elapsed_time(t1) * 1e-3
+        self._events = []
+        return self.Timer
+
+    def step(self):
+        for diag in self.diags:
+            diag.make_record(self.it)
+
+        self.timer_start()
+        for frame in self.frames:
+            if np.mod(self.it, frame.Args['Steps']) == 0:
+                frame.shift_grids(grids=self.solvers)
+                frame.inject_plasma(species=self.species, grid=self.mainsolver)
+        self.timer_record('frame')
+
+        self._push_and_sort()
+
+        self.timer_start()
+        for solver in self.solvers:
+            solver.depose_currents(species=self.species)
+        self.timer_record('depose')
+
+        self._push_and_sort()
+
+        for solver in self.solvers:
+            self.timer_start()
+            solver.depose_charge(species=self.species)
+            self.timer_record('depose')
+
+            self.timer_start()
+            solver.fb_transform(scals=['rho', ], vects=['J', ], dir=0)
+            self.timer_record('transform')
+
+            self.timer_start()
+            solver.fields_smooth(flds=['rho', 'Jx', 'Jy', 'Jz'])
+            self.timer_record('smooth')
+
+            self.timer_start()
+            for m in range(0, solver.Args['M'] + 1):
+                for comp in solver.Args['vec_comps']:
+                    key = comp + '_fb_m' + str(m)
+                    # dN0 <- dN1: swap the buffers instead of copying them
+                    # (field_grad overwrites every element of dN1 right after)
+                    solver.DataDev['dN0' + key], solver.DataDev['dN1' + key] = \
+                        solver.DataDev['dN1' + key], solver.DataDev['dN0' + key]
+            self.timer_record('data_copy')
+
+            self.timer_start()
+            solver.field_grad('rho', 'dN1')
+            self.timer_record('grad')
+
+            self.timer_start()
+            solver.push_fields()
+            self.timer_record('push-eb')
+
+            self.timer_start()
+            solver.damp_fields()
+            self.timer_record('damp-eb')
+
+            self.timer_start()
+            solver.restore_B_fb()
+            self.timer_record('restore_B')
+
+            self.timer_start()
+            solver.fb_transform(vects=['E', 'B'], dir=1)
+            self.timer_record('transform')
+
+            self.timer_start()
+            solver.gather_and_push(species=self.species)
+            self.timer_record('gather + push-p')
+
+        for parts in self.species:
+            parts.free_mp()
+
+        self.it += 1
+        return self.it
+
+    def _push_and_sort(self):
+        for parts in self.species:
+            self.timer_start()
+            parts.push_coords(mode='half')
+            self.timer_record('push-x')
+
+            self.timer_start()
+            parts.sort_parts(grid=self.mainsolver)
+            self.timer_record('sort')

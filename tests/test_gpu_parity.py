@@ -1,0 +1,375 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the reference-shaped Python
+API) against the oracle on identical seeded inputs, and against the committed golden
+vectors produced from the reference's own kernels.
+
+Tolerances (stated per check): integer products and the coordinate push are
+bit-exact; gather + Boris is bit-exact given identical fields; depositions
+<= 1e-12 * max|field| (summation order differs); single transforms / spectral
+operators <= 1e-12 relative to max; full steps <= 1e-10.
+"""
+import numpy as np
+import pytest
+
+from oracle import orchestration as O
+from oracle.np_kernels import NumpyKernels
+
+from helpers import ATTR, golden_cfgs, load_golden, oracle_case_from_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+INT_KEYS = ("indx_in_cell", "sum_in_cell", "cell_offset", "sort_indx")
+
+
+@pytest.fixture(scope="module")
+def comm():
+    from chimeracl_b200.methods.generic_methods_cl import Communicator
+    return Communicator(answers=[0, 0], seed=7)
+
+
+def gpu_case_from_golden(G, comm):
+    from chimeracl_b200.particles import Particles
+    from chimeracl_b200.solver import Solver
+    cfg, pcfg = golden_cfgs(G)
+    S = Solver(dict(cfg), comm)
+    for k in G.files:
+        if k.startswith("in/S/"):
+            S.DataDev[k[5:]][:] = G[k]
+    P = Particles(dict(pcfg), comm)
+    I = Particles(dict(pcfg, charge=1, Immobile=True), comm)
+    set_particles(P, {a: G["in/P/" + a] for a in ATTR})
+    set_particles(I, {a: G["in/P/" + a] for a in ("x", "y", "z", "w")})
+    return S, P, I
+
+
+def set_particles(P, arrays):
+    from chimeracl_b200.devarray import DevArray
+    for a in P._attr_names():
+        P.DataDev[a] = DevArray.from_numpy(np.ascontiguousarray(arrays[a], dtype=np.float64),
+                                           P.comm.device)
+    P.reset_num_parts()
+    P.flag_sorted = False
+
+
+def check_sort_products(P, Po):
+    assert int(P.Args["Np_stay"]) == Po.Args["Np_stay"]
+    for k in INT_KEYS:
+        assert np.array_equal(P.DataDev[k].get(), Po.D[k]), k
+
+
+# ----------------------------------------------------------------------------- particles
+@pytest.mark.parametrize("M", [0, 1])
+@pytest.mark.parametrize("fused", [False, True])
+def test_push_and_sort_bit_exact(comm, M, fused):
+    G = load_golden(M)
+    S, P, I = gpu_case_from_golden(G, comm)
+    So, Po, Io = oracle_case_from_golden(G, NumpyKernels(M))
+    P.fuse_push_sort = fused
+    for p, po in ((P, Po), (I, Io)):
+        p.push_coords("half")
+        p.sort_parts(S)
+        po.push_coords("half")
+        po.sort_parts(So)
+    for k in ("x", "y", "z"):
+        assert np.array_equal(P.DataDev[k].get(), Po.D[k]), k
+    check_sort_products(P, Po)
+    check_sort_products(I, Io)
+    # golden vectors (reference kernels): same products
+    for k in INT_KEYS:
+        assert np.array_equal(P.DataDev[k].get(), G["sort1/P/" + k]), k
+    # align: gather by the permutation, drop the trash tail
+    P.align_parts()
+    Po.align_parts()
+    assert P.Args["Np"] == Po.Args["Np"]
+    for k in ATTR:
+        assert np.array_equal(P.DataDev[k].get(), Po.D[k]), k
+    assert np.array_equal(P.DataDev["sort_indx"].get(), Po.D["sort_indx"])
+
+
+def _random_species(comm, n, box, seed, spread=1.0):
+    from chimeracl_b200.particles import Particles
+    rng = np.random.default_rng(seed)
+    arrays = {"x": rng.uniform(box[0], box[1], n), "y": rng.normal(0, spread, n),
+              "z": rng.normal(0, spread, n), "px": rng.normal(0, 1, n),
+              "py": rng.normal(0, 1, n), "pz": rng.normal(0, 1, n),
+              "w": rng.uniform(0.5, 1.5, n)}
+    arrays["g_inv"] = 1 / np.sqrt(1 + arrays["px"] ** 2 + arrays["py"] ** 2 + arrays["pz"] ** 2)
+    P = Particles({"charge": -1, "dt": 0.01}, comm)
+    set_particles(P, arrays)
+    Po = O.OracleParticles({"charge": -1, "dt": 0.01}, NumpyKernels(1))
+    Po.set_particles(**arrays)
+    return P, Po
+
+
+@pytest.mark.parametrize("shape,n", [((8, 6), 300000),     # ~10^4 per cell: giant segments
+                                     ((64, 40), 400000),   # ~160 per cell: bitonic path
+                                     ((256, 128), 500000), # ~15 per cell: insertion path
+                                     ((16, 8), 37)])       # fewer particles than a warp
+def test_sort_random_order_stable(comm, shape, n):
+    """Storage in random order (worst case for the run-aggregated scatter): the
+    permutation must still be the stable one, including the trash-bin tail."""
+    from chimeracl_b200.solver import Solver
+    Nx, Nr = shape
+    cfg = {"Xmin": -1.0, "Xmax": 1.0, "Nx": Nx, "Rmin": 0.0, "Rmax": 1.0, "Nr": Nr, "M": 1}
+    S = Solver(dict(cfg), comm)
+    So = O.OracleSolver(dict(cfg), NumpyKernels(1))
+    P, Po = _random_species(comm, n, (-1.2, 1.2), seed=n, spread=0.5)
+    P.sort_parts(S)
+    Po.sort_parts(So)
+    check_sort_products(P, Po)
+    assert Po.D["sum_in_cell"][-1] > 0          # the trash bin is populated
+    # idempotence: sorting the aligned particles gives the identity permutation
+    P.align_parts()
+    P.flag_sorted = False
+    P.sort_parts(S)
+    assert np.array_equal(P.DataDev["sort_indx"].get(), np.arange(P.Args["Np"], dtype=np.uint32))
+
+
+def test_sort_edge_cases(comm):
+    from chimeracl_b200.particles import Particles
+    from chimeracl_b200.solver import Solver
+    cfg = {"Xmin": 0.0, "Xmax": 1.0, "Nx": 8, "Rmin": 0.0, "Rmax": 1.0, "Nr": 6, "M": 1}
+    S = Solver(dict(cfg), comm)
+    P = Particles({"charge": -1}, comm)
+    P.sort_parts(S)                        # empty species: no-op
+    assert P.flag_sorted and "sort_indx" not in P.DataDev
+    n = 50
+    far = np.full(n, 10.0)
+    set_particles(P, {a: far for a in ATTR})
+    P.sort_parts(S)                        # everything in the trash bin
+    assert P.Args["Np_stay"] == 0
+    assert np.array_equal(P.DataDev["sort_indx"].get(), np.arange(n))
+    P.align_parts()
+    assert P.Args["Np"] == 0 and P.DataDev["x"].size == 0
+    nan = np.full(4, np.nan)
+    set_particles(P, {a: nan for a in ATTR})
+    P.sort_parts(S)                        # NaN coordinates -> trash bin
+    assert P.Args["Np_stay"] == 0
+
+
+# ----------------------------------------------------------------------------- grid
+@pytest.mark.parametrize("M", [0, 1])
+def test_deposit_and_gather(comm, M):
+    G = load_golden(M)
+    S, P, I = gpu_case_from_golden(G, comm)
+    So, Po, Io = oracle_case_from_golden(G, NumpyKernels(M))
+    rng = np.random.default_rng(11)
+    for k in sorted(So.D):
+        if k[0] in "EB" and "_fb_" not in k:
+            a = rng.normal(size=So.D[k].shape)
+            if So.D[k].dtype == np.complex128:
+                a = a + 1j * rng.normal(size=a.shape)
+            So.D[k][...] = a
+            S.DataDev[k][:] = a
+    for p, po, s, so in ((P, Po, S, So), (I, Io, S, So)):
+        p.push_coords("half")
+        p.sort_parts(s)
+        po.push_coords("half")
+        po.sort_parts(so)
+    S.depose_currents([P, I])
+    S.depose_charge([P, I])
+    So.depose_currents([Po, Io])
+    So.depose_charge([Po, Io])
+    for k in So.D:
+        if k.startswith(("rho_m", "Jx_m", "Jy_m", "Jz_m")):
+            assert rel_err(S.DataDev[k].get(), So.D[k]) < 1e-12, k
+    S.gather_and_push([P, I])
+    So.gather_and_push([Po, Io])
+    for k in So.D:
+        if k[0] in "EB" and "_fb_" not in k:     # ghost rows written by warp_axis
+            assert np.array_equal(S.DataDev[k].get(), So.D[k]), k
+    for k in ("px", "py", "pz", "g_inv"):
+        got, ref = P.DataDev[k].get(), Po.D[k]
+        assert np.array_equal(got, ref), (k, np.abs(got - ref).max())
+
+
+def test_deposit_dense_cells(comm):
+    """Many particles per cell (batches of the staged deposit wrap several times)."""
+    from chimeracl_b200.solver import Solver
+    cfg = {"Xmin": -1.0, "Xmax": 1.0, "Nx": 12, "Rmin": 0.0, "Rmax": 1.0, "Nr": 9, "M": 1}
+    S = Solver(dict(cfg), comm)
+    So = O.OracleSolver(dict(cfg), NumpyKernels(1))
+    P, Po = _random_species(comm, 200000, (-1.1, 1.1), seed=3, spread=0.4)
+    P.sort_parts(S)
+    Po.sort_parts(So)
+    S.depose_currents([P])
+    S.depose_charge([P])
+    So.depose_currents([Po])
+    So.depose_charge([Po])
+    for k in So.D:
+        if k.startswith(("rho_m", "Jx_m", "Jy_m", "Jz_m")):
+            assert rel_err(S.DataDev[k].get(), So.D[k]) < 1e-12, k
+
+
+# ----------------------------------------------------------------------------- spectral
+@pytest.mark.parametrize("n", [8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192,
+                               30, 100, 900, 1000, 1537])
+def test_fft_against_numpy(comm, n):
+    from chimeracl_b200.devarray import DevArray
+    from chimeracl_b200.solver import Solver
+    cfg = {"Xmin": -1.0, "Xmax": 1.3, "Nx": n, "Rmin": 0.0, "Rmax": 1.0, "Nr": 6, "M": 1}
+    S = Solver(dict(cfg), comm)
+    rng = np.random.default_rng(n)
+    a = rng.normal(size=(5, n)) + 1j * rng.normal(size=(5, n))
+    src = DevArray.from_numpy(a, comm.device)
+    dst = DevArray.zeros((5, n), np.complex128, comm.device)
+    S._fft(dst, src, 0)
+    assert rel_err(dst.get(), np.fft.fft(a, axis=1)) < 5e-14
+    S._fft(dst, src, 1)
+    assert rel_err(dst.get(), np.fft.ifft(a, axis=1)) < 5e-14
+    S._fft(src, src, 0)      # in place
+    assert rel_err(src.get(), np.fft.fft(a, axis=1)) < 5e-14
+
+
+@pytest.mark.parametrize("K,N", [(5, 8), (89, 900), (127, 130), (128, 64), (255, 2048), (511, 333)])
+def test_dht_contraction_against_numpy(comm, K, N):
+    from chimeracl_b200.devarray import DevArray
+    from chimeracl_b200.solver import Solver
+    cfg = {"Xmin": -1.0, "Xmax": 1.0, "Nx": 16, "Rmin": 0.0, "Rmax": 1.0, "Nr": 6, "M": 1}
+    S = Solver(dict(cfg), comm)
+    rng = np.random.default_rng(K * 1000 + N)
+    A = rng.normal(size=(K, K))
+    Br = rng.normal(size=(K + 1, N))
+    Bc = rng.normal(size=(K + 1, N)) + 1j * rng.normal(size=(K + 1, N))
+    dA = DevArray.from_numpy(A, comm.device)
+    for B in (Br, Bc):
+        dB = DevArray.from_numpy(B, comm.device)
+        dC = DevArray.zeros((K + 1, N), B.dtype, comm.device)
+        S._dot(dC[1:], dA, dB[1:])                 # row-offset views on both sides
+        ref = A.dot(B[1:])
+        assert rel_err(dC.get()[1:], ref) < 1e-13
+        assert not dC.get()[0].any()
+    # fused two-output epilogue: y = -b, z += -i b
+    dB = DevArray.from_numpy(Bc[1:].copy(), comm.device)
+    y = DevArray.zeros((K, N), np.complex128, comm.device)
+    z0 = rng.normal(size=(K, N)) + 1j * rng.normal(size=(K, N))
+    z = DevArray.from_numpy(z0, comm.device)
+    S._cdot2(dA, dB, y, -1.0, False, z, -1j, True)
+    b = A.dot(Bc[1:])
+    assert rel_err(y.get(), -b) < 1e-13
+    assert rel_err(z.get(), z0 - 1j * b) < 1e-13
+
+
+@pytest.mark.parametrize("M", [0, 1])
+def test_spectral_pipeline_against_oracle(comm, M):
+    """fb_transform fwd, smoothing, grad, PSATD advance, damping, rot + Poisson,
+    fb_transform bwd -- each compared with the oracle on identical inputs."""
+    G = load_golden(M)
+    S, _, _ = gpu_case_from_golden(G, comm)
+    So, _, _ = oracle_case_from_golden(G, NumpyKernels(M))
+    rng = np.random.default_rng(21)
+    for k in sorted(So.D):
+        if k.startswith(("rho_m", "Jx_m", "Jy_m", "Jz_m")) or k.startswith(("dN1", "dN0")):
+            a = rng.normal(size=So.D[k].shape)
+            if So.D[k].dtype == np.complex128:
+                a = a + 1j * rng.normal(size=a.shape)
+            So.D[k][...] = a
+            S.DataDev[k][:] = a
+
+    def compare(keys, tol, what):
+        for k in So.D:
+            if k.startswith(keys):
+                e = rel_err(S.DataDev[k].get(), So.D[k])
+                assert e < tol, (what, k, e)
+
+    for s in (S, So):
+        s.fb_transform(scals=["rho"], vects=["J"], dir=0)
+    compare(("rho_fb", "Jx_fb", "Jy_fb", "Jz_fb"), 1e-12, "forward")
+    for s in (S, So):
+        s.fields_smooth(["rho", "Jx", "Jy", "Jz"])
+        s.field_grad("rho", "dN1")
+    compare(("dN1",), 1e-12, "grad")
+    for s in (S, So):
+        s.push_fields()
+    compare(("Ex_fb", "Ey_fb", "Ez_fb", "Gx_fb", "Gy_fb", "Gz_fb"), 1e-12, "psatd")
+    for s in (S, So):
+        s.damp_fields()
+    compare(("Ex_fb", "Ey_fb", "Ez_fb", "Gx_fb", "Gy_fb", "Gz_fb"), 1e-12, "damp")
+    for s in (S, So):
+        s.restore_B_fb()
+    compare(("Bx_fb", "By_fb", "Bz_fb"), 1e-12, "rot+poisson")
+    for s in (S, So):
+        s.fb_transform(vects=["E", "B"], dir=1)
+    compare(("Ex_m", "Ey_m", "Ez_m", "Bx_m", "By_m", "Bz_m"), 1e-12, "backward")
+    if M == 1:
+        for s in (S, So):
+            s.field_div("E", "rho")
+        compare(("rho_fb",), 1e-12, "div")
+
+
+# ----------------------------------------------------------------------------- full step
+@pytest.mark.parametrize("M", [0, 1])
+def test_pic_steps_against_golden(comm, M):
+    """Two full PIC_loop.step() calls against the reference-kernel golden run."""
+    from chimeracl_b200.pic_loop import PIC_loop
+    G = load_golden(M)
+    S, P, I = gpu_case_from_golden(G, comm)
+    loop = PIC_loop(solvers=[S], species=[P, I], frames=[], diags=[])
+    loop.step()
+    for k in G.files:
+        if k.startswith("step1/S/"):
+            assert rel_err(S.DataDev[k[8:]].get(), G[k]) < 1e-10, k
+        elif k.startswith("step1/P/"):
+            assert rel_err(P.DataDev[k[8:]].get(), G[k]) < 1e-10, k
+    loop.step()
+    P.align_parts()
+    for k in G.files:
+        if k.startswith("step2_aligned/S/"):
+            assert rel_err(S.DataDev[k[16:]].get(), G[k]) < 1e-10, k
+        elif k.startswith("step2_aligned/P/"):
+            name = k[16:]
+            got = P.DataDev[name].get()
+            if name == "sort_indx":
+                assert np.array_equal(got, G[k])
+            else:
+                assert rel_err(got, G[k]) < 1e-10, k
+
+
+def test_transformer_round_trip_cfg2(comm):
+    """examples/test_transformer.py at BASELINE config 2 (Nx=2048, Nr=256, M=1): beam
+    -> sort -> align -> depose_charge -> forward -> zero -> backward; error formula
+    of test_transformer.py:40-43, stated tolerance 1e-12."""
+    from chimeracl_b200.particles import Particles
+    from chimeracl_b200.solver import Solver
+    grid_in = {"Xmin": -1., "Xmax": 1., "Nx": 2048, "Rmin": 0, "Rmax": 1., "Nr": 256, "M": 1}
+    parts = Particles(grid_in, comm)
+    grid = Solver(grid_in, comm)
+    beam_in = {"Np": int(7e6), "FullCharge": 1, "x_c": 0., "Lx": 0.3, "y_c": 0.2, "Ly": 0.3,
+               "z_c": 0.2, "Lz": 0.3}
+    parts.add_particles(beam_in=beam_in)
+    parts.sort_parts(grid=grid)
+    parts.align_parts()
+    grid.depose_charge([parts, ])
+    tmp0 = grid.DataDev["rho_m0"].get().copy()
+    tmp1 = grid.DataDev["rho_m1"].get().copy()
+    grid.fb_transform(scals=["rho", ], dir=0)
+    grid.set_to(grid.DataDev["rho_m0"], 0)
+    grid.set_to(grid.DataDev["rho_m1"], 0)
+    grid.fb_transform(scals=["rho", ], dir=1)
+    err = (np.abs(grid.DataDev["rho_m0"].get() - tmp0)[1:] / np.abs(tmp0[1:]).max()
+           + np.abs(grid.DataDev["rho_m1"].get() - tmp1)[1:] / np.abs(tmp1[1:]).max()).max()
+    assert err < 1e-12, err
+
+
+def test_laser_group_velocity(comm):
+    """examples/test_laser_veloc.py (M=0 vacuum) at reduced size: same property and
+    bound as tests/test_oracle.py::test_laser_group_velocity_property."""
+    from chimeracl_b200.laser import add_gausian_pulse
+    from chimeracl_b200.solver import Solver
+    cfg = {"Xmin": -40.0, "Xmax": 40.0, "Rmax": 40.0, "M": 0}
+    dx, dr, cfg["dt"] = 0.1, 0.5, 0.1
+    cfg["Nx"] = int((cfg["Xmax"] - cfg["Xmin"]) / dx) // 2 * 2
+    cfg["Nr"] = int(cfg["Rmax"] / dr) // 2 * 2 + 1
+    solver = Solver(cfg, comm)
+    laser = {"k0": 1.0, "a0": 1.0, "x0": 0, "Lx": 8.0, "R": 8.0, "x_foc": 10.0}
+    add_gausian_pulse(solver, laser)
+    xc = []
+    for _ in range(40):
+        solver.push_fields()
+        solver.fb_transform(scals=["Ez"], dir=1)
+        v = solver.DataDev["Ez_m0"].get()
+        Px = (solver.Args["Rgrid"][1:, None] * v[1:, :] ** 2).sum(0)
+        xc.append((solver.Args["Xgrid"] * Px).sum() / Px.sum())
+    xc = np.array(xc)
+    veloc = 1 - (xc[1:] - xc[:-1]) / solver.Args["dt"]
+    theory = (2.0 * np.pi * laser["R"]) ** -2
+    assert abs(veloc.mean() - theory) / theory < 0.1
