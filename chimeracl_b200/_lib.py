@@ -51,6 +51,55 @@ SIGNATURES = {
 _lib = None
 
 
+class _LibProxy:
+    """Attribute access returns the ctypes entry points; enable_profiling() swaps in
+    wrappers that bracket every call with CUDA events on the current stream (used by
+    bench.py to time individual kernels inside a real step)."""
+
+    def __init__(self, cdll):
+        self._cdll = cdll
+        self._raw = {}
+        self._events = []
+
+    def _install(self, name, fn):
+        self._raw[name] = fn
+        object.__setattr__(self, name, fn)
+
+    def enable_profiling(self, names=None):
+        import torch
+        for name, fn in self._raw.items():
+            if not name.startswith("chb_") or fn.restype is not _i32 or not fn.argtypes \
+                    or fn.argtypes[-1] is not _vp:
+                continue
+            if names is not None and name not in names:
+                continue
+
+            def timed(*args, _fn=fn, _name=name):
+                e0 = torch.cuda.Event(enable_timing=True)
+                e1 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+                rc = _fn(*args)
+                e1.record()
+                self._events.append((_name, e0, e1))
+                return rc
+            object.__setattr__(self, name, timed)
+
+    def disable_profiling(self):
+        for name, fn in self._raw.items():
+            object.__setattr__(self, name, fn)
+
+    def profile_report(self):
+        """{name: (calls, total_ms)}; synchronises."""
+        import torch
+        torch.cuda.synchronize()
+        out = {}
+        for name, e0, e1 in self._events:
+            n, t = out.get(name, (0, 0.0))
+            out[name] = (n + 1, t + e0.elapsed_time(e1))
+        self._events = []
+        return out
+
+
 def load():
     global _lib
     if _lib is not None:
@@ -59,16 +108,28 @@ def load():
         raise RuntimeError(
             "chimera_b200: %s is missing -- build it with `python -m chimeracl_b200.build` "
             "(there is no CPU fallback)" % LIB_PATH)
-    lib = ctypes.CDLL(LIB_PATH)
+    cdll = ctypes.CDLL(LIB_PATH)
+    lib = _LibProxy(cdll)
     for name, (res, args) in SIGNATURES.items():
-        fn = getattr(lib, name)      # AttributeError if the symbol is not exported
+        fn = getattr(cdll, name)     # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
+        lib._install(name, fn)
     _lib = lib
     return lib
 
 
+# kernel launches behind each C-ABI call (bench.py reports the total as gpu_launches)
+KERNELS_PER_CALL = {"chb_cell_offsets": 3, "chb_sort_scatter_stable": 3, "chb_align": 2}
+CALL_COUNTS = {}
+
+
+def launches():
+    return sum(n * KERNELS_PER_CALL.get(k, 1) for k, n in CALL_COUNTS.items())
+
+
 def check(rc, what=""):
+    CALL_COUNTS[what] = CALL_COUNTS.get(what, 0) + 1
     if rc != 0:
         msg = load().chb_error_string(int(rc)).decode()
         raise RuntimeError("chimera_b200 %s failed: %s (code %d)" % (what, msg, rc))

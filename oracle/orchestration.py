@@ -330,6 +330,29 @@ class OracleSolver:
                 K.append_c2c(oy, b)
                 K.zpaxz(oz, -1j, b)
 
+    def field_div(self, vin, sout):
+        """transformer_methods_cl.py:135-183 (unused by the loop, part of the API)."""
+        A, D, K, M = self.Args, self.D, self.K, self.M
+        for c in "yz":
+            self._get_mm1(vin + c, c)
+        b0 = np.empty((A["Nr"] - 1, A["Nx"]), dtype=np.complex128)
+        for m in range(M + 1):
+            out = D["%s_fb_m%d" % (sout, m)]
+            out[...] = 0
+            K.ab_dot_x(1j, A["kx"], D["%sx_fb_m%d" % (vin, m)], out, A["NxNrm1"], A["Nx"])
+            if m > 0:
+                fy, fz = (D["%s%s_fb_m%d" % (vin, c, m - 1)] for c in "yz")
+            elif M > 0:
+                fy, fz = D["buff_fb_m-1_y"], D["buff_fb_m-1_z"]
+            else:
+                continue
+            K.axpbyz(-1j, fz, -1.0, fy, b0)
+            K.append_c2c(out, np.ascontiguousarray(np.dot(A["dDHT_minus_m%d" % m], b0)))
+            if m < M:
+                fy, fz = (D["%s%s_fb_m%d" % (vin, c, m + 1)] for c in "yz")
+                K.axpbyz(-1j, fz, 1.0, fy, b0)
+                K.append_c2c(out, np.ascontiguousarray(np.dot(A["dDHT_plus_m%d" % m], b0)))
+
     def field_rot(self, fin, fout):
         """transformer_methods_cl.py:185-263."""
         A, D, K, M = self.Args, self.D, self.K, self.M
