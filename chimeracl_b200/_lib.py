@@ -28,7 +28,7 @@ SIGNATURES = {
     "chb_depose_vector": (_i32, [_i32] + [_vp] * 10 + [_i32, _u32, _u32] + [_vp] * 4 + [_vp, _vp]),
     "chb_postproc_depose": (_i32, [_vp, _vp, _i32, _u32, _u32, _vp, _vp]),
     "chb_warp_axis": (_i32, [_vp, _vp, _i32, _u32, _vp]),
-    "chb_gather_push": (_i32, [_i32] + [_vp] * 9 + [_u32, _vp, _u32, _u32] + [_vp] * 4 + [_vp, _vp]),
+    "chb_gather_push": (_i32, [_i32] + [_vp] * 10 + [_u32, _vp, _u32, _u32] + [_vp] * 4 + [_vp, _vp]),
     "chb_cast_c2d": (_i32, [_vp, _vp, _sz, _vp]),
     "chb_cast_d2c": (_i32, [_vp, _vp, _sz, _vp]),
     "chb_append_c2c": (_i32, [_vp, _vp, _sz, _vp]),
@@ -44,6 +44,9 @@ SIGNATURES = {
     "chb_dht": (_i32, [_vp, _u32, _vp, _u32, _vp, _u32, _u32, _u32, _u32, _i32, _dbl, _dbl, _i32, _vp]),
     "chb_dht2": (_i32, [_vp, _u32, _vp, _u32, _vp, _dbl, _dbl, _i32, _vp, _dbl, _dbl, _i32,
                         _u32, _u32, _u32, _u32, _i32, _vp]),
+    "chb_dht_batched": (_i32, [_vp, _u32, _vp, _vp, _i32, _u32, _u32, _u32, _u32, _u32, _i32, _vp]),
+    "chb_fft_x_batched": (_i32, [_vp, _vp, _i32, _u32, _u32, _sz, _sz, _i32, _i32, _i32, _vp, _i32,
+                                 _vp, _u32, _vp, _vp, _vp]),
     "chb_fft_max_pow2": (_i32, []),
     "chb_fft_x": (_i32, [_vp, _vp, _u32, _u32, _sz, _sz, _i32, _i32, _i32, _vp, _i32, _vp, _u32, _vp, _vp, _vp]),
 }

@@ -18,13 +18,13 @@ OBJ_DIR = os.path.join(HERE, "build")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
           "-I", os.path.join(ROOT, "include")]
-# per-file extra flags: gather.cu mirrors the reference's operation order without
-# FMA contraction so that the Boris push is bit-comparable with the oracle.
+# per-file extra flags (none at present; integer-deciding arithmetic uses explicit
+# round-to-nearest intrinsics instead of a global -fmad=false)
 SOURCES = {
     "capi.cu": [],
     "particles.cu": [],
     "deposit.cu": [],
-    "gather.cu": ["-fmad=false"],
+    "gather.cu": [],
     "spectral.cu": [],
     "dht.cu": [],
     "fft.cu": [],

@@ -11,9 +11,9 @@
 //   * phase 1 (thread per particle, coalesced through sort_indx): load the
 //     attributes once, do the expensive per-particle math (sqrt, 1/r, scaled
 //     coordinates) and stage 5-8 doubles per particle in shared memory;
-//   * phase 2 (thread per cell): accumulate the cell's 2x2 node stencil for all
-//     components/modes in registers from shared memory (padded layout, no bank
-//     conflicts for ~uniform fillings) -- no atomics at all inside a cell;
+//   * phase 2 (thread per cell and component): accumulate the cell's 2x2 node
+//     stencil for all modes in registers from shared memory (padded layout, no
+//     bank conflicts for ~uniform fillings) -- no atomics at all inside a cell;
 //   * one FP64 RED per node value and CELL (not per particle) to the L2.
 // The four colour passes, their launches and the memsets between them are gone;
 // sums agree with the reference up to FP64 summation order.
@@ -46,10 +46,19 @@ struct DepArgs {
   uint32_t ncells;
 };
 
+// Threads per CTA: one thread per (cell, component) -- the three current components
+// of a cell are accumulated by three threads (each in a different warp, so the
+// component index is warp-uniform), which keeps the accumulators at 4*(1+2M) doubles
+// per thread and the occupancy high.
+template <bool VEC>
+struct DepShape { static constexpr int kThreads = kDepCells * (VEC ? 3 : 1); };
+
 template <int M, bool VEC>
-__global__ void __launch_bounds__(kDepCells)
+__global__ void __launch_bounds__(DepShape<VEC>::kThreads, VEC ? 3 : 6)
 depose_kernel(DepArgs<M, VEC> a) {
   constexpr int NC = VEC ? 3 : 1;
+  constexpr int NT = DepShape<VEC>::kThreads;
+  constexpr int MM = M > 0 ? M : 1;
   constexpr int NSTAGE = 3 + (VEC ? 3 : 0) + (M > 0 ? 2 : 0);
   __shared__ double stage[NSTAGE][kDepPad];
 
@@ -62,7 +71,8 @@ depose_kernel(DepArgs<M, VEC> a) {
   const uint32_t P0 = a.cell_offset[c0], P1 = a.cell_offset[c1];
   if (P0 == P1) return;
 
-  const uint32_t c = c0 + threadIdx.x;
+  const int comp = threadIdx.x / kDepCells;           // warp-uniform
+  const uint32_t c = c0 + (threadIdx.x - comp * kDepCells);
   uint32_t S = 0, E = 0;
   int ix = 0, ir = 0;
   if (c < c1) {
@@ -73,23 +83,17 @@ depose_kernel(DepArgs<M, VEC> a) {
   }
   const double dix = (double)ix, dir_ = (double)ir;
 
-  double acc0[NC][4];
-  double accm[M > 0 ? NC : 1][M > 0 ? M : 1][4][2];
+  double acc0[4] = {0.0, 0.0, 0.0, 0.0};
+  double accm[MM][4][2];
 #pragma unroll
-  for (int k = 0; k < NC; ++k)
+  for (int m = 0; m < MM; ++m)
 #pragma unroll
-    for (int n = 0; n < 4; ++n) {
-      acc0[k][n] = 0.0;
-      if (M > 0) {
-#pragma unroll
-        for (int m = 0; m < (M > 0 ? M : 1); ++m) { accm[k][m][n][0] = 0.0; accm[k][m][n][1] = 0.0; }
-      }
-    }
+    for (int n = 0; n < 4; ++n) accm[m][n][0] = accm[m][n][1] = 0.0;
 
   for (uint32_t b0 = P0; b0 < P1; b0 += kDepBatch) {
     const uint32_t b1 = min(b0 + (uint32_t)kDepBatch, P1);
-    // ---------------- phase 1: thread per particle
-    for (uint32_t j = b0 + threadIdx.x; j < b1; j += kDepCells) {
+    // ---------------- phase 1: thread per particle (all threads of the CTA)
+    for (uint32_t j = b0 + threadIdx.x; j < b1; j += NT) {
       const uint32_t s = __ldg(a.sort_indx + j);
       const double xp = __ldg(a.x + s), yp = __ldg(a.y + s), zp = __ldg(a.z + s);
       double wp;
@@ -114,7 +118,7 @@ depose_kernel(DepArgs<M, VEC> a) {
       }
     }
     __syncthreads();
-    // ---------------- phase 2: thread per cell
+    // ---------------- phase 2: thread per (cell, component)
     const uint32_t js = max(S, b0), je = min(E, b1);
     for (uint32_t j = js; j < je; ++j) {
       const int p = pidx((int)(j - b0));
@@ -125,31 +129,31 @@ depose_kernel(DepArgs<M, VEC> a) {
       const double sR0 = __dsub_rn(1.0, sR1);
       sX0 = __dmul_rn(sX0, wp);
       sX1 = __dmul_rn(sX1, wp);
-      double C[4] = {__dmul_rn(sR0, sX0), __dmul_rn(sR0, sX1),
-                     __dmul_rn(sR1, sX0), __dmul_rn(sR1, sX1)};
-      double er[M > 0 ? M : 1], ei[M > 0 ? M : 1];
+      const double jk = VEC ? stage[3 + comp][p] : 1.0;
+      double pj[4] = {__dmul_rn(sR0, sX0), __dmul_rn(sR0, sX1),
+                      __dmul_rn(sR1, sX0), __dmul_rn(sR1, sX1)};
+      if (VEC) {
+#pragma unroll
+        for (int n = 0; n < 4; ++n) pj[n] = __dmul_rn(pj[n], jk);
+      }
+      double er[MM], ei[MM];
       if (M > 0) {
         er[0] = stage[NSTAGE - 2][p];
         ei[0] = stage[NSTAGE - 1][p];
 #pragma unroll
-        for (int m = 1; m < (M > 0 ? M : 1); ++m) {  // e^{i(m+1)theta}
+        for (int m = 1; m < MM; ++m) {  // e^{i(m+1)theta}
           er[m] = er[m - 1] * er[0] - ei[m - 1] * ei[0];
           ei[m] = er[m - 1] * ei[0] + ei[m - 1] * er[0];
         }
       }
 #pragma unroll
-      for (int k = 0; k < NC; ++k) {
-        const double jk = VEC ? stage[3 + k][p] : 1.0;
+      for (int n = 0; n < 4; ++n) {
+        acc0[n] = __dadd_rn(acc0[n], pj[n]);
+        if (M > 0) {
 #pragma unroll
-        for (int n = 0; n < 4; ++n) {
-          const double pj = VEC ? __dmul_rn(C[n], jk) : C[n];
-          acc0[k][n] = __dadd_rn(acc0[k][n], pj);
-          if (M > 0) {
-#pragma unroll
-            for (int m = 0; m < (M > 0 ? M : 1); ++m) {
-              accm[k][m][n][0] = fma(pj, er[m], accm[k][m][n][0]);
-              accm[k][m][n][1] = fma(pj, ei[m], accm[k][m][n][1]);
-            }
+          for (int m = 0; m < MM; ++m) {
+            accm[m][n][0] = fma(pj[n], er[m], accm[m][n][0]);
+            accm[m][n][1] = fma(pj[n], ei[m], accm[m][n][1]);
           }
         }
       }
@@ -162,16 +166,13 @@ depose_kernel(DepArgs<M, VEC> a) {
 #pragma unroll
     for (int n = 0; n < 4; ++n) {
       const size_t node = (size_t)(ix + (n & 1)) + (size_t)(ir + (n >> 1)) * (size_t)g.Nx;
+      red_add_f64(a.out[comp] + node, acc0[n]);
+      if (M > 0) {
 #pragma unroll
-      for (int k = 0; k < NC; ++k) {
-        red_add_f64(a.out[k] + node, acc0[k][n]);
-        if (M > 0) {
-#pragma unroll
-          for (int m = 0; m < (M > 0 ? M : 1); ++m) {
-            double* o = a.out[(m + 1) * NC + k] + 2 * node;
-            red_add_f64(o, accm[k][m][n][0]);
-            red_add_f64(o + 1, accm[k][m][n][1]);
-          }
+        for (int m = 0; m < MM; ++m) {
+          double* o = a.out[(m + 1) * NC + comp] + 2 * node;
+          red_add_f64(o, accm[m][n][0]);
+          red_add_f64(o + 1, accm[m][n][1]);
         }
       }
     }
@@ -181,7 +182,7 @@ depose_kernel(DepArgs<M, VEC> a) {
 template <int M, bool VEC>
 static int launch_depose(DepArgs<M, VEC>& a, cudaStream_t st) {
   uint32_t grid = (a.ncells + kDepCells - 1) / kDepCells;
-  depose_kernel<M, VEC><<<grid, kDepCells, 0, st>>>(a);
+  depose_kernel<M, VEC><<<grid, DepShape<VEC>::kThreads, 0, st>>>(a);
   CHB_RETURN_LAST_ERROR();
 }
 

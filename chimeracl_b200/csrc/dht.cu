@@ -33,8 +33,8 @@ __device__ __forceinline__ void dmma_884(double& c0, double& c1, double a, doubl
 
 struct GemmArgs {
   const double* __restrict__ A;
-  const double* __restrict__ B;
-  double* __restrict__ C;
+  const double* Bv[CHB_MAX_FIELDS];   // batched right-hand sides (blockIdx.z)
+  double* Cv[CHB_MAX_FIELDS];
   uint32_t lda, ldb, ldc;   // in doubles
   uint32_t M, N, K;         // N in doubles (2*Nx for complex data)
   double alpha_re, alpha_im;
@@ -69,10 +69,14 @@ __device__ __forceinline__ void gemm_store(double* c, double v0, double v1, doub
   }
 }
 
+constexpr int kSlabDoubles = BM * LDA_S + BK * LDB_S;
+constexpr int kGemmSmem = 2 * kSlabDoubles * (int)sizeof(double);   // double buffered
+
 __global__ void __launch_bounds__(kGemmThreads, 2)
 dht_gemm_kernel(GemmArgs p) {
-  __shared__ double As[BM * LDA_S];
-  __shared__ double Bs[BK * LDB_S];
+  extern __shared__ double gemm_smem[];
+  const double* __restrict__ Bg = p.Bv[blockIdx.z];
+  double* __restrict__ Cg = p.Cv[blockIdx.z];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
@@ -95,10 +99,12 @@ dht_gemm_kernel(GemmArgs p) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const uint32_t gc = n0 + b_col + i;
-      rb[i] = (gk < p.K && gc < p.N) ? __ldg(p.B + (size_t)gk * p.ldb + gc) : 0.0;
+      rb[i] = (gk < p.K && gc < p.N) ? __ldg(Bg + (size_t)gk * p.ldb + gc) : 0.0;
     }
   };
-  auto store_slab = [&]() {
+  auto store_slab = [&](int buf) {
+    double* As = gemm_smem + buf * kSlabDoubles;
+    double* Bs = As + BM * LDA_S;
 #pragma unroll
     for (int i = 0; i < 8; ++i) As[a_row * LDA_S + a_k + i] = ra[i];
 #pragma unroll
@@ -112,11 +118,14 @@ dht_gemm_kernel(GemmArgs p) {
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
   load_slab(0);
+  store_slab(0);
+  __syncthreads();
+  int cur = 0;
   for (uint32_t k0 = 0; k0 < p.K; k0 += BK) {
-    __syncthreads();          // previous slab fully consumed
-    store_slab();
-    __syncthreads();
-    if (k0 + BK < p.K) load_slab(k0 + BK);   // prefetch while multiplying
+    const bool more = k0 + BK < p.K;
+    if (more) load_slab(k0 + BK);   // global loads in flight while multiplying
+    const double* As = gemm_smem + cur * kSlabDoubles;
+    const double* Bs = As + BM * LDA_S;
 #pragma unroll
     for (int kk = 0; kk < BK; kk += 4) {
       double a[4], b[4];
@@ -129,6 +138,9 @@ dht_gemm_kernel(GemmArgs p) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) dmma_884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
+    if (more) store_slab(cur ^ 1);  // the other buffer was consumed one iteration ago
+    __syncthreads();
+    cur ^= 1;
   }
 
   // epilogue: thread owns C(row g, cols 2t, 2t+1) of every 8x8 block
@@ -141,7 +153,7 @@ dht_gemm_kernel(GemmArgs p) {
       const uint32_t col = n0 + wn * 32 + j * 8 + 2 * t;
       if (col >= p.N) continue;
       const bool pair = (col + 1 < p.N);
-      gemm_store(p.C + (size_t)row * p.ldc + col, acc[i][j][0], acc[i][j][1], p.alpha_re,
+      gemm_store(Cg + (size_t)row * p.ldc + col, acc[i][j][0], acc[i][j][1], p.alpha_re,
                  p.alpha_im, p.complex_pairs, p.accumulate, pair);
       if (p.C2)
         gemm_store(p.C2 + (size_t)row * p.ldc2 + col, acc[i][j][0], acc[i][j][1], p.alpha2_re,
@@ -154,19 +166,25 @@ dht_gemm_kernel(GemmArgs p) {
 
 using namespace chb;
 
-static int dht_launch(const double* A, uint32_t lda, const double* B, uint32_t ldb,
-                      double* C, uint32_t ldc, uint32_t M, uint32_t K, uint32_t N,
+static int dht_launch(const double* A, uint32_t lda, const double* const* Bv, int nbatch,
+                      uint32_t ldb, double* const* Cv, uint32_t ldc, uint32_t M, uint32_t K,
+                      uint32_t N,
                       int is_complex, double alpha_re, double alpha_im, int accumulate,
                       double* C2, uint32_t ldc2, double alpha2_re, double alpha2_im,
                       int accumulate2, void* stream) {
-  if (M == 0 || N == 0) return CHB_OK;
+  if (M == 0 || N == 0 || nbatch == 0) return CHB_OK;
+  if (nbatch < 0 || nbatch > CHB_MAX_FIELDS || (C2 && nbatch != 1)) return CHB_ERR_ARG;
   if (!is_complex && (alpha_im != 0.0 || alpha2_im != 0.0)) return CHB_ERR_ARG;
   GemmArgs p;
+  for (int k = 0; k < CHB_MAX_FIELDS; ++k) {
+    p.Bv[k] = k < nbatch ? Bv[k] : nullptr;
+    p.Cv[k] = k < nbatch ? Cv[k] : nullptr;
+  }
   p.C2 = C2;
   p.ldc2 = is_complex ? 2 * ldc2 : ldc2;
   p.alpha2_re = alpha2_re; p.alpha2_im = alpha2_im;
   p.accumulate2 = accumulate2;
-  p.A = A; p.B = B; p.C = C;
+  p.A = A;
   p.lda = lda;
   p.ldb = is_complex ? 2 * ldb : ldb;
   p.ldc = is_complex ? 2 * ldc : ldc;
@@ -175,8 +193,15 @@ static int dht_launch(const double* A, uint32_t lda, const double* B, uint32_t l
   p.alpha_re = alpha_re; p.alpha_im = alpha_im;
   p.complex_pairs = is_complex;
   p.accumulate = accumulate;
-  dim3 grid((p.N + BN - 1) / BN, (M + BM - 1) / BM);
-  dht_gemm_kernel<<<grid, kGemmThreads, 0, (cudaStream_t)stream>>>(p);
+  dim3 grid((p.N + BN - 1) / BN, (M + BM - 1) / BM, nbatch);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(dht_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         kGemmSmem);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  dht_gemm_kernel<<<grid, kGemmThreads, kGemmSmem, (cudaStream_t)stream>>>(p);
   CHB_RETURN_LAST_ERROR();
 }
 
@@ -184,14 +209,21 @@ extern "C" int chb_dht(const double* A, uint32_t lda, const double* B, uint32_t 
                        double* C, uint32_t ldc, uint32_t M, uint32_t K, uint32_t N,
                        int is_complex, double alpha_re, double alpha_im, int accumulate,
                        void* stream) {
-  return dht_launch(A, lda, B, ldb, C, ldc, M, K, N, is_complex, alpha_re, alpha_im,
+  return dht_launch(A, lda, &B, 1, ldb, &C, ldc, M, K, N, is_complex, alpha_re, alpha_im,
                     accumulate, nullptr, 0, 1.0, 0.0, 0, stream);
+}
+
+extern "C" int chb_dht_batched(const double* A, uint32_t lda, const double* const* B_host,
+                               double* const* C_host, int nbatch, uint32_t ldb, uint32_t ldc,
+                               uint32_t M, uint32_t K, uint32_t N, int is_complex, void* stream) {
+  return dht_launch(A, lda, B_host, nbatch, ldb, C_host, ldc, M, K, N, is_complex, 1.0, 0.0, 0,
+                    nullptr, 0, 1.0, 0.0, 0, stream);
 }
 
 extern "C" int chb_dht2(const double* A, uint32_t lda, const double* B, uint32_t ldb,
                         double* C1, double a1_re, double a1_im, int accumulate1, double* C2,
                         double a2_re, double a2_im, int accumulate2, uint32_t ldc, uint32_t M,
                         uint32_t K, uint32_t N, int is_complex, void* stream) {
-  return dht_launch(A, lda, B, ldb, C1, ldc, M, K, N, is_complex, a1_re, a1_im, accumulate1,
-                    C2, ldc, a2_re, a2_im, accumulate2, stream);
+  return dht_launch(A, lda, &B, 1, ldb, &C1, ldc, M, K, N, is_complex, a1_re, a1_im,
+                    accumulate1, C2, ldc, a2_re, a2_im, accumulate2, stream);
 }

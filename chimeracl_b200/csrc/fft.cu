@@ -7,11 +7,15 @@
 // (kernels/transformer_generic.cl:58-80; :306-311, :344-348), the real-part
 // extraction cast_array_c2d (:351) and the [1:] row-slice copies (:295, :358).
 //
-// One CTA transforms one row entirely in shared memory (N*16 bytes): a Stockham
-// autosort FFT with radix-8 passes (plus one radix-4/2 pass), every thread
-// holding 8 complex values in registers per pass, so one buffer suffices.
-// HBM traffic is the compulsory 16 B read + 16 B write per point (8 B when one
-// side is real); the prologue/epilogue ops ride along for free.
+// One CTA transforms one row entirely in shared memory: a Stockham autosort FFT
+// with radix-8 passes (plus one radix-4/2 pass), every thread holding 8 complex
+// values in REGISTERS per pass (transform length is a template parameter, so all
+// loops unroll and nothing spills to local memory) and one padded buffer
+// (index i -> i + i/8, which makes the stride-8 stores of the first pass
+// conflict-free).  Several arrays (components / modes of one fb_transform call)
+// go into one launch (blockIdx.y), which removes the wave-quantisation loss of
+// Nr-1 ~ 511 rows on 148 SMs.  HBM/L2 traffic is the compulsory 16 B read +
+// 16 B write per point (8 B when one side is real).
 // Lengths that are not powers of two (the reference's Nx=900 example) use
 // Bluestein's chirp-z algorithm on top of the same in-smem power-of-two FFT.
 #include "common.cuh"
@@ -54,69 +58,76 @@ __device__ __forceinline__ void dft8(double2* v) {
   v[1] = d0; v[3] = d1; v[5] = d2; v[7] = d3;
 }
 
-// In-place forward FFT of s[0..N) in shared memory, N = 2^logN >= 8, executed by
-// exactly N/8 threads (tid in [0, N/8)); other threads of the CTA only hit the
-// barriers.  tw[j] = exp(-2 pi i j / N).
-__device__ void fft_smem_forward(double2* s, int N, int logN, const double2* __restrict__ tw,
-                                 int tid, bool active) {
-  const int T = N >> 3;
-  int Ns = 1;
-  int done = 0;
-  while (done < logN) {
-    const int rem = logN - done;
-    const int lr = rem >= 3 ? 3 : rem;   // log2 of this pass's radix
-    const int R = 1 << lr;
-    const int nb = 8 >> lr;              // butterflies per thread
-    double2 v[8];
-    if (active) {
+__device__ __forceinline__ int pad(int i) { return i + (i >> 3); }
+__host__ __device__ constexpr int padded_len(int n) { return n + (n >> 3); }
+
+// One Stockham pass of radix 2^LR at sub-transform length NS over s[0..N).
+template <int LOGN, int LR, int NS>
+__device__ __forceinline__ void stockham_pass(double2* s, const double2* __restrict__ tw, int tid) {
+  constexpr int N = 1 << LOGN, T = N >> 3, R = 1 << LR, NB = 8 >> LR;
+  double2 v[8];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        if (q < nb) {
-          const int j = tid + q * T;
-          for (int r = 0; r < R; ++r) v[q * R + r] = s[j + r * (N / R)];
-        }
-      }
-    }
-    __syncthreads();
-    if (active) {
+  for (int q = 0; q < NB; ++q) {
+    const int j = tid + q * T;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        if (q < nb) {
-          const int j = tid + q * T;
-          const int k = j & (Ns - 1);
-          double2* b = v + q * R;
-          if (Ns > 1) {
-            const double2 w1 = __ldg(tw + (size_t)k * (N / (Ns * R)));
-            double2 w = w1;
-            for (int r = 1; r < R; ++r) {
-              b[r] = cmulf(b[r], w);
-              if (r + 1 < R) w = cmulf(w, w1);
-            }
-          }
-          if (lr == 3) dft8(b);
-          else if (lr == 2) dft4(b[0], b[1], b[2], b[3]);
-          else dft2(b[0], b[1]);
-          const int j0 = ((j - k) << lr) + k;   // (j / Ns) * Ns * R + k
-          for (int r = 0; r < R; ++r) s[j0 + r * Ns] = b[r];
-        }
-      }
-    }
-    __syncthreads();
-    Ns <<= lr;
-    done += lr;
+    for (int r = 0; r < R; ++r) v[q * R + r] = s[pad(j + r * (N / R))];
   }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < NB; ++q) {
+    const int j = tid + q * T;
+    const int k = j & (NS - 1);
+    double2* b = v + q * R;
+    if (NS > 1) {
+      const double2 w1 = __ldg(tw + (size_t)k * (N / (NS * R)));
+      double2 w = w1;
+#pragma unroll
+      for (int r = 1; r < R; ++r) {
+        b[r] = cmulf(b[r], w);
+        if (r + 1 < R) w = cmulf(w, w1);
+      }
+    }
+    if (LR == 3) dft8(b);
+    else if (LR == 2) dft4(b[0], b[1], b[2], b[3]);
+    else dft2(b[0], b[1]);
+    const int j0 = ((j - k) << LR) + k;   // (j / NS) * NS * R + k
+#pragma unroll
+    for (int r = 0; r < R; ++r) s[pad(j0 + r * NS)] = b[r];
+  }
+  __syncthreads();
+}
+
+template <int LOGN, int DONE, int NS>
+struct Passes {
+  static __device__ __forceinline__ void run(double2* s, const double2* __restrict__ tw, int tid) {
+    constexpr int REM = LOGN - DONE;
+    constexpr int LR = REM >= 3 ? 3 : REM;
+    stockham_pass<LOGN, LR, NS>(s, tw, tid);
+    Passes<LOGN, DONE + LR, (NS << LR)>::run(s, tw, tid);
+  }
+};
+template <int LOGN, int NS>
+struct Passes<LOGN, LOGN, NS> {
+  static __device__ __forceinline__ void run(double2*, const double2* __restrict__, int) {}
+};
+
+// In-place forward FFT of the padded buffer s (natural order in, natural order
+// out), executed by exactly N/8 threads; tw[j] = exp(-2 pi i j / N).
+template <int LOGN>
+__device__ __forceinline__ void fft_smem_forward(double2* s, const double2* __restrict__ tw, int tid) {
+  Passes<LOGN, 0, 1>::run(s, tw, tid);
 }
 
 struct FftArgs {
-  const double* in;      // real or complex rows
-  double* out;
+  const double* in[CHB_MAX_FIELDS];   // real or complex rows, one entry per batched array
+  double* out[CHB_MAX_FIELDS];
   size_t in_stride;      // elements between rows (of the input element type)
   size_t out_stride;
   const double2* tw;     // N (or L for Bluestein) forward roots of unity
   const double2* phase;  // Nx entries or nullptr
   const double2* chirp;  // Bluestein: exp(-i pi n^2 / N), n < N
   const double2* bfft;   // Bluestein: FFT_L(b)/L
-  int N, L, logL;
+  int N;
   int inverse;           // normalised inverse transform
   int in_real, out_real; // element types
   int phase_in;          // multiply the input by phase[ix] (backward path) ...
@@ -138,33 +149,66 @@ __device__ __forceinline__ void store_out(const FftArgs& a, double* row, int ix,
   else reinterpret_cast<double2*>(row)[ix] = v;
 }
 
-__global__ void fft_pow2_kernel(FftArgs a) {
+template <int LOGN>
+__global__ void __launch_bounds__((1 << LOGN) / 8 < 32 ? 32 : (1 << LOGN) / 8)
+fft_pow2_kernel(FftArgs a) {
   extern __shared__ double2 s[];
-  const int N = a.N, T = N >> 3, tid = threadIdx.x;
-  const double* rin = a.in + (size_t)blockIdx.x * a.in_stride * (a.in_real ? 1 : 2);
-  double* rout = a.out + (size_t)blockIdx.x * a.out_stride * (a.out_real ? 1 : 2);
-  for (int i = tid; i < N; i += blockDim.x) s[i] = load_in(a, rin, i);
+  constexpr int N = 1 << LOGN, T = N >> 3;
+  const int tid = threadIdx.x;
+  const double* rin = a.in[blockIdx.y] + (size_t)blockIdx.x * a.in_stride * (a.in_real ? 1 : 2);
+  double* rout = a.out[blockIdx.y] + (size_t)blockIdx.x * a.out_stride * (a.out_real ? 1 : 2);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int i = tid + q * T;
+    s[pad(i)] = load_in(a, rin, i);
+  }
   __syncthreads();
-  fft_smem_forward(s, N, a.logL, a.tw, tid, tid < T);
-  for (int i = tid; i < N; i += blockDim.x) store_out(a, rout, i, s[i]);
+  fft_smem_forward<LOGN>(s, a.tw, tid);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int i = tid + q * T;
+    store_out(a, rout, i, s[pad(i)]);
+  }
 }
 
-__global__ void fft_bluestein_kernel(FftArgs a) {
+template <int LOGL>
+__global__ void __launch_bounds__((1 << LOGL) / 8 < 32 ? 32 : (1 << LOGL) / 8)
+fft_bluestein_kernel(FftArgs a) {
   extern __shared__ double2 s[];
-  const int N = a.N, L = a.L, T = L >> 3, tid = threadIdx.x;
-  const double* rin = a.in + (size_t)blockIdx.x * a.in_stride * (a.in_real ? 1 : 2);
-  double* rout = a.out + (size_t)blockIdx.x * a.out_stride * (a.out_real ? 1 : 2);
-  for (int i = tid; i < L; i += blockDim.x)
-    s[i] = i < N ? cmulf(load_in(a, rin, i), __ldg(a.chirp + i)) : make_double2(0.0, 0.0);
+  constexpr int L = 1 << LOGL, T = L >> 3;
+  const int N = a.N, tid = threadIdx.x;
+  const double* rin = a.in[blockIdx.y] + (size_t)blockIdx.x * a.in_stride * (a.in_real ? 1 : 2);
+  double* rout = a.out[blockIdx.y] + (size_t)blockIdx.x * a.out_stride * (a.out_real ? 1 : 2);
+  for (int i = tid; i < L; i += T)
+    s[pad(i)] = i < N ? cmulf(load_in(a, rin, i), __ldg(a.chirp + i)) : make_double2(0.0, 0.0);
   __syncthreads();
-  fft_smem_forward(s, L, a.logL, a.tw, tid, tid < T);
+  fft_smem_forward<LOGL>(s, a.tw, tid);
   // pointwise product with FFT(b)/L, conjugated so that the second forward FFT
   // acts as the inverse: ifft(z) = conj(fft(conj(z)))
-  for (int i = tid; i < L; i += blockDim.x) s[i] = cconj(cmulf(s[i], __ldg(a.bfft + i)));
+  for (int i = tid; i < L; i += T) s[pad(i)] = cconj(cmulf(s[pad(i)], __ldg(a.bfft + i)));
   __syncthreads();
-  fft_smem_forward(s, L, a.logL, a.tw, tid, tid < T);
-  for (int i = tid; i < N; i += blockDim.x)
-    store_out(a, rout, i, cmulf(cconj(s[i]), __ldg(a.chirp + i)));
+  fft_smem_forward<LOGL>(s, a.tw, tid);
+  for (int i = tid; i < N; i += T)
+    store_out(a, rout, i, cmulf(cconj(s[pad(i)]), __ldg(a.chirp + i)));
+}
+
+template <int LOGL>
+static int launch_fft(const FftArgs& a, bool pow2, uint32_t rows, int nbatch, cudaStream_t st) {
+  constexpr int L = 1 << LOGL;
+  const int threads = L / 8;   // >= 1; kernels index with tid < L/8 only
+  const size_t smem = (size_t)padded_len(L) * sizeof(double2);
+  cudaError_t e;
+  dim3 grid(rows, nbatch);
+  if (pow2) {
+    e = cudaFuncSetAttribute(fft_pow2_kernel<LOGL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    fft_pow2_kernel<LOGL><<<grid, threads, smem, st>>>(a);
+  } else {
+    e = cudaFuncSetAttribute(fft_bluestein_kernel<LOGL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    fft_bluestein_kernel<LOGL><<<grid, threads, smem, st>>>(a);
+  }
+  CHB_RETURN_LAST_ERROR();
 }
 
 }  // namespace chb
@@ -175,44 +219,57 @@ extern "C" {
 
 int chb_fft_max_pow2(void) { return 8192; }
 
-int chb_fft_x(const double* in, double* out, uint32_t rows, uint32_t Nx, size_t in_stride,
-              size_t out_stride, int inverse, int in_real, int out_real,
-              const double* phase, int phase_on_input, const double* twiddles,
-              uint32_t L, const double* chirp, const double* bfft, void* stream) {
-  if (rows == 0 || Nx == 0) return CHB_OK;
+int chb_fft_x_batched(const double* const* in_host, double* const* out_host, int nbatch,
+                      uint32_t rows, uint32_t Nx, size_t in_stride, size_t out_stride,
+                      int inverse, int in_real, int out_real, const double* phase,
+                      int phase_on_input, const double* twiddles, uint32_t L,
+                      const double* chirp, const double* bfft, void* stream) {
+  if (rows == 0 || Nx == 0 || nbatch == 0) return CHB_OK;
+  if (nbatch < 0 || nbatch > CHB_MAX_FIELDS) return CHB_ERR_ARG;
   if (L < 8 || (L & (L - 1)) || L > 8192) return CHB_ERR_ARG;
   const bool pow2 = (L == Nx);
   if (!pow2 && (L < 2 * Nx - 1 || !chirp || !bfft)) return CHB_ERR_ARG;
   FftArgs a;
-  a.in = in; a.out = out;
+  for (int k = 0; k < CHB_MAX_FIELDS; ++k) {
+    a.in[k] = k < nbatch ? in_host[k] : nullptr;
+    a.out[k] = k < nbatch ? out_host[k] : nullptr;
+  }
   a.in_stride = in_stride; a.out_stride = out_stride;
   a.tw = (const double2*)twiddles;
   a.phase = (const double2*)phase;
   a.chirp = (const double2*)chirp;
   a.bfft = (const double2*)bfft;
-  a.N = (int)Nx; a.L = (int)L;
-  a.logL = 0;
-  while ((1u << a.logL) < L) ++a.logL;
+  a.N = (int)Nx;
   a.inverse = inverse;
   a.in_real = in_real; a.out_real = out_real;
   a.phase_in = (phase && phase_on_input) ? 1 : 0;
   a.phase_out = (phase && !phase_on_input) ? 1 : 0;
   a.scale = inverse ? 1.0 / (double)Nx : 1.0;
-  int threads = (int)(L >> 3);
-  if (threads < 32) threads = 32;
-  size_t smem = (size_t)L * sizeof(double2);
+  int logL = 0;
+  while ((1u << logL) < L) ++logL;
   cudaStream_t st = (cudaStream_t)stream;
-  cudaError_t e;
-  if (pow2) {
-    e = cudaFuncSetAttribute(fft_pow2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    fft_pow2_kernel<<<rows, threads, smem, st>>>(a);
-  } else {
-    e = cudaFuncSetAttribute(fft_bluestein_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    fft_bluestein_kernel<<<rows, threads, smem, st>>>(a);
+  switch (logL) {
+    case 3: return launch_fft<3>(a, pow2, rows, nbatch, st);
+    case 4: return launch_fft<4>(a, pow2, rows, nbatch, st);
+    case 5: return launch_fft<5>(a, pow2, rows, nbatch, st);
+    case 6: return launch_fft<6>(a, pow2, rows, nbatch, st);
+    case 7: return launch_fft<7>(a, pow2, rows, nbatch, st);
+    case 8: return launch_fft<8>(a, pow2, rows, nbatch, st);
+    case 9: return launch_fft<9>(a, pow2, rows, nbatch, st);
+    case 10: return launch_fft<10>(a, pow2, rows, nbatch, st);
+    case 11: return launch_fft<11>(a, pow2, rows, nbatch, st);
+    case 12: return launch_fft<12>(a, pow2, rows, nbatch, st);
+    case 13: return launch_fft<13>(a, pow2, rows, nbatch, st);
+    default: return CHB_ERR_ARG;
   }
-  CHB_RETURN_LAST_ERROR();
+}
+
+int chb_fft_x(const double* in, double* out, uint32_t rows, uint32_t Nx, size_t in_stride,
+              size_t out_stride, int inverse, int in_real, int out_real,
+              const double* phase, int phase_on_input, const double* twiddles,
+              uint32_t L, const double* chirp, const double* bfft, void* stream) {
+  return chb_fft_x_batched(&in, &out, 1, rows, Nx, in_stride, out_stride, inverse, in_real,
+                           out_real, phase, phase_on_input, twiddles, L, chirp, bfft, stream);
 }
 
 }  // extern "C"

@@ -248,15 +248,21 @@ constexpr int kFixBlock = 256;   // cells per CTA, one thread per cell
 constexpr int kFixCap = 8192;    // staged entries (32 KiB)
 constexpr int kSmall = 48;
 
-__device__ void bitonic_sort_smem(uint32_t* a, int n) {
+// Shared staging buffer is addressed through SP(): one pad word every 16 entries, so
+// that threads walking their own ~16-entry segments (stride ~16 words between lanes)
+// hit different banks instead of the same one.
+#define SP(i) ((i) + ((i) >> 4))
+constexpr int kFixCapPadded = kFixCap + kFixCap / 16 + 1;
+
+__device__ void bitonic_sort_smem(uint32_t* a, int base, int n) {
   int P = 1;
   while (P < n) P <<= 1;
   for (int k = 2; k <= P; k <<= 1) {
     for (int i = threadIdx.x; i < P; i += blockDim.x) {
       int l = i ^ (k - 1);
       if (l > i && l < n) {
-        uint32_t u = a[i], v = a[l];
-        if (u > v) { a[i] = v; a[l] = u; }
+        uint32_t u = a[SP(base + i)], v = a[SP(base + l)];
+        if (u > v) { a[SP(base + i)] = v; a[SP(base + l)] = u; }
       }
     }
     __syncthreads();
@@ -264,13 +270,29 @@ __device__ void bitonic_sort_smem(uint32_t* a, int n) {
       for (int i = threadIdx.x; i < P; i += blockDim.x) {
         int l = i ^ j;
         if (l > i && l < n) {
-          uint32_t u = a[i], v = a[l];
-          if (u > v) { a[i] = v; a[l] = u; }
+          uint32_t u = a[SP(base + i)], v = a[SP(base + l)];
+          if (u > v) { a[SP(base + i)] = v; a[SP(base + l)] = u; }
         }
       }
       __syncthreads();
     }
   }
+}
+
+// insertion sort of a[base .. base+n) addressed through SP() (shared staging)
+__device__ __forceinline__ bool insertion_sort_sp(uint32_t* a, int base, int n) {
+  bool changed = false;
+  uint32_t prev = a[SP(base)];
+  for (int i = 1; i < n; ++i) {
+    uint32_t v = a[SP(base + i)];
+    if (prev <= v) { prev = v; continue; }
+    changed = true;
+    int j = i - 1;
+    while (j >= 0 && a[SP(base + j)] > v) { a[SP(base + j + 1)] = a[SP(base + j)]; --j; }
+    a[SP(base + j + 1)] = v;
+    // prev stays the maximum so far (a[base+i] after the shift)
+  }
+  return changed;
 }
 
 __device__ __forceinline__ bool insertion_sort(uint32_t* a, int n) {
@@ -290,7 +312,7 @@ __global__ void __launch_bounds__(kFixBlock)
 sort_fixup_kernel(const uint32_t* __restrict__ cell_offset, uint32_t nbins,
                   uint32_t* __restrict__ sort_indx, uint32_t* __restrict__ giant_count,
                   uint32_t* __restrict__ giant_list, uint32_t giant_cap) {
-  __shared__ uint32_t stage[kFixCap];
+  __shared__ uint32_t stage[kFixCapPadded];
   __shared__ uint32_t big_list[kFixBlock];
   __shared__ uint32_t big_n;
   __shared__ int any_changed;
@@ -308,11 +330,11 @@ sort_fixup_kernel(const uint32_t* __restrict__ cell_offset, uint32_t nbins,
 
     if (hi - lo <= (uint32_t)kFixCap) {
       // stage the whole range (coalesced), sort segments in shared memory
-      for (uint32_t i = threadIdx.x; i < hi - lo; i += kFixBlock) stage[i] = sort_indx[lo + i];
+      for (uint32_t i = threadIdx.x; i < hi - lo; i += kFixBlock) stage[SP(i)] = sort_indx[lo + i];
       __syncthreads();
       if (nseg > 1) {
         if (nseg <= (uint32_t)kSmall) {
-          if (insertion_sort(stage + (s - lo), (int)nseg)) any_changed = 1;
+          if (insertion_sort_sp(stage, (int)(s - lo), (int)nseg)) any_changed = 1;
         } else {
           big_list[atomicAdd(&big_n, 1u)] = threadIdx.x;
         }
@@ -322,12 +344,12 @@ sort_fixup_kernel(const uint32_t* __restrict__ cell_offset, uint32_t nbins,
       for (uint32_t b = 0; b < nb; ++b) {
         uint32_t t = big_list[b];
         uint32_t bs = cell_offset[c0 + t], be = cell_offset[c0 + t + 1];
-        bitonic_sort_smem(stage + (bs - lo), (int)(be - bs));
+        bitonic_sort_smem(stage, (int)(bs - lo), (int)(be - bs));
       }
       if (nb) any_changed = 1;
       __syncthreads();
       if (any_changed)
-        for (uint32_t i = threadIdx.x; i < hi - lo; i += kFixBlock) sort_indx[lo + i] = stage[i];
+        for (uint32_t i = threadIdx.x; i < hi - lo; i += kFixBlock) sort_indx[lo + i] = stage[SP(i)];
       __syncthreads();
     } else {
       // crowded range: small segments in place in global memory (each thread
@@ -346,10 +368,10 @@ sort_fixup_kernel(const uint32_t* __restrict__ cell_offset, uint32_t nbins,
         uint32_t bs = cell_offset[c0 + t], be = cell_offset[c0 + t + 1];
         uint32_t bn = be - bs;
         if (bn <= (uint32_t)kFixCap) {
-          for (uint32_t i = threadIdx.x; i < bn; i += kFixBlock) stage[i] = sort_indx[bs + i];
+          for (uint32_t i = threadIdx.x; i < bn; i += kFixBlock) stage[SP(i)] = sort_indx[bs + i];
           __syncthreads();
-          bitonic_sort_smem(stage, (int)bn);
-          for (uint32_t i = threadIdx.x; i < bn; i += kFixBlock) sort_indx[bs + i] = stage[i];
+          bitonic_sort_smem(stage, 0, (int)bn);
+          for (uint32_t i = threadIdx.x; i < bn; i += kFixBlock) sort_indx[bs + i] = stage[SP(i)];
           __syncthreads();
         } else if (threadIdx.x == 0) {
           uint32_t k = atomicAdd(giant_count, 1u);

@@ -105,5 +105,5 @@ class GridMethodsCL(GenericMethodsCL):
             raise RuntimeError("gather_and_push needs sorted particles (call sort_parts first)")
         self._call('chb_gather_push', int(self.Args['M']), P['x'].ptr, P['y'].ptr, P['z'].ptr,
                    P['px'].ptr, P['py'].ptr, P['pz'].ptr, P['g_inv'].ptr, P['sort_indx'].ptr,
-                   P['FactorPush'].ptr, Np, P['Np_stay_dev'].ptr, *self._geom(),
+                   P['cell_offset'].ptr, P['FactorPush'].ptr, Np, P['Np_stay_dev'].ptr, *self._geom(),
                    _lib.ptr_array(ptrs))

@@ -68,14 +68,21 @@ class TransformerMethodsCL(GenericMethodsCL):
         self._fft_bfft = DevArray.from_numpy(bfft, dev) if bfft is not None else None
 
     def _fft_rows(self, src, dst, direction, phase=None, in_real=False, out_real=False):
-        """dst = FFT_x(src) row by row; src/dst are 2-D DevArrays (views allowed)."""
-        rows, Nx = src.shape
-        self._call('chb_fft_x', src.ptr, dst.ptr, rows, Nx, src.t.stride(0), dst.t.stride(0),
-                   1 if direction == 1 else 0, int(in_real), int(out_real),
-                   phase.ptr if phase is not None else None,
-                   1 if direction == 1 else 0, self._fft_tw.ptr, self._fft_L,
-                   self._fft_chirp.ptr if self._fft_chirp is not None else None,
-                   self._fft_bfft.ptr if self._fft_bfft is not None else None)
+        """dst = FFT_x(src) row by row; src/dst are 2-D DevArrays (views allowed) or
+        equally long lists of them (one batched launch)."""
+        srcs = src if isinstance(src, (list, tuple)) else [src]
+        dsts = dst if isinstance(dst, (list, tuple)) else [dst]
+        rows, Nx = srcs[0].shape
+        for i in range(0, len(srcs), 16):
+            sl, dl = srcs[i:i + 16], dsts[i:i + 16]
+            self._call('chb_fft_x_batched', _lib.ptr_array([a.ptr for a in sl]),
+                       _lib.ptr_array([a.ptr for a in dl]), len(sl), rows, Nx,
+                       sl[0].t.stride(0), dl[0].t.stride(0),
+                       1 if direction == 1 else 0, int(in_real), int(out_real),
+                       phase.ptr if phase is not None else None,
+                       1 if direction == 1 else 0, self._fft_tw.ptr, self._fft_L,
+                       self._fft_chirp.ptr if self._fft_chirp is not None else None,
+                       self._fft_bfft.ptr if self._fft_bfft is not None else None)
 
     def _fft(self, arr_out, arr, dir):
         """Plain FFT along axis 1 (numpy conventions, normalised inverse): the
@@ -108,52 +115,79 @@ class TransformerMethodsCL(GenericMethodsCL):
                    a1.imag, int(acc1), c2.ptr, a2.real, a2.imag, int(acc2), c1.t.stride(0),
                    M, K, N, 1)
 
+    def _dot_batched(self, cs, a, bs):
+        """cs[k] = a . bs[k] for equally shaped right-hand sides, one launch."""
+        cplx = bs[0].dtype == np.complex128
+        M, K = a.shape
+        N = bs[0].shape[1]
+        for i in range(0, len(bs), 16):
+            bl, cl = bs[i:i + 16], cs[i:i + 16]
+            self._call('chb_dht_batched', a.ptr, a.t.stride(0),
+                       _lib.ptr_array([x.ptr for x in bl]), _lib.ptr_array([x.ptr for x in cl]),
+                       len(bl), bl[0].t.stride(0), cl[0].t.stride(0), M, K, N, int(cplx))
+
     # ------------------------------------------------------------------ transforms
+    def _phase(self, dir):
+        """exp(-+ i kx Xmin) from the HOST Xmin (moving-window aware, reference
+        :40-44); recomputed only when Xmin changed."""
+        xmin = float(self.Args['Xmin'])
+        cache = self.__dict__.setdefault('_phase_cache', {})
+        hit = cache.get(dir)
+        if hit is None or hit[0] != xmin:
+            arr = hit[1] if hit is not None else DevArray.empty(self.Args['Nx'], np.complex128,
+                                                                self.comm.device)
+            self._call('chb_get_phase', arr.ptr, self.DataDev['kx'].ptr, xmin, int(dir),
+                       int(self.Args['Nx']))
+            cache[dir] = (xmin, arr)
+            hit = cache[dir]
+        self.DataDev['phs_shft'] = hit[1]
+        return hit[1]
+
+    def _tmp(self, kind, n):
+        """Pool of (Nr-1, Nx) scratch arrays for batched transforms."""
+        pool = self.__dict__.setdefault('_tmp_pool', {'d': [], 'c': []})[kind]
+        shape = (self.Args['Nr'] - 1, self.Args['Nx'])
+        while len(pool) < n:
+            pool.append(DevArray.empty(shape, np.double if kind == 'd' else np.complex128,
+                                       self.comm.device))
+        return pool[:n]
+
     def transform_field(self, arg_cmp, dir, mode):
-        D = self.DataDev
-        # phase from the HOST Xmin (moving-window aware), reference :40-44
-        self._call('chb_get_phase', D['phs_shft'].ptr, D['kx'].ptr, float(self.Args['Xmin']),
-                   int(dir), int(self.Args['Nx']))
-        if dir == 0:
-            op = self._transform_forward if mode == 'full' else self._half_transform_forward
-            op('DHT_m', arg_cmp + '_m', arg_cmp + '_fb_m', D['phs_shft'])
-        elif dir == 1:
-            op = self._transform_backward if mode == 'full' else self._half_transform_backward
-            op('DHT_inv_m', arg_cmp + '_fb_m', arg_cmp + '_m', D['phs_shft'])
+        self.transform_fields([arg_cmp], dir, mode)
 
-    def _transform_forward(self, dht_arg, arg_in, arg_out, phs_shft):
+    def transform_fields(self, comps, dir, mode):
+        """Forward (dir=0) / backward (dir=1) Fourier-Bessel transform of several
+        components at once: per azimuthal mode one batched DHT and one batched FFT
+        launch (mode='half': FFT only).  Same arithmetic per component as
+        reference transformer_methods_cl.py:290-455."""
+        if not comps:
+            return
         D = self.DataDev
+        phs = self._phase(dir)
+        full = (mode == 'full')
+        n = len(comps)
         for m in range(self.Args['M'] + 1):
-            src = D[arg_in + str(m)][1:]
-            if m == 0:
-                self._dot(D['fld_buff1_d'], D[dht_arg + '0'], src)
-                self._fft_rows(D['fld_buff1_d'], D[arg_out + '0'], 0, phs_shft, in_real=True)
+            ms = str(m)
+            real = (m == 0)
+            grid = [D[c + '_m' + ms][1:] for c in comps]
+            spec = [D[c + '_fb_m' + ms] for c in comps]
+            if dir == 0:
+                if not full:
+                    self._fft_rows(grid, spec, 0, phs, in_real=real)
+                elif real:
+                    tmp = self._tmp('d', n)
+                    self._dot_batched(tmp, D['DHT_m0'], grid)
+                    self._fft_rows(tmp, spec, 0, phs, in_real=True)
+                else:
+                    self._dot_batched(spec, D['DHT_m' + ms], grid)
+                    self._fft_rows(spec, spec, 0, phs)          # in place
             else:
-                self._dot(D['fld_buff0_c'], D[dht_arg + str(m)], src)
-                self._fft_rows(D['fld_buff0_c'], D[arg_out + str(m)], 0, phs_shft)
-
-    def _transform_backward(self, dht_arg, arg_in, arg_out, phs_shft):
-        D = self.DataDev
-        for m in range(self.Args['M'] + 1):
-            dst = D[arg_out + str(m)][1:]
-            if m == 0:
-                self._fft_rows(D[arg_in + '0'], D['fld_buff0_d'], 1, phs_shft, out_real=True)
-                self._dot(dst, D[dht_arg + '0'], D['fld_buff0_d'])
-            else:
-                self._fft_rows(D[arg_in + str(m)], D['fld_buff0_c'], 1, phs_shft)
-                self._dot(dst, D[dht_arg + str(m)], D['fld_buff0_c'])
-
-    def _half_transform_backward(self, dht_arg, arg_in, arg_out, phs_shft):
-        D = self.DataDev
-        for m in range(self.Args['M'] + 1):
-            self._fft_rows(D[arg_in + str(m)], D[arg_out + str(m)][1:], 1, phs_shft,
-                           out_real=(m == 0))
-
-    def _half_transform_forward(self, dht_arg, arg_in, arg_out, phs_shft):
-        D = self.DataDev
-        for m in range(self.Args['M'] + 1):
-            self._fft_rows(D[arg_in + str(m)][1:], D[arg_out + str(m)], 0, phs_shft,
-                           in_real=(m == 0))
+                if not full:
+                    self._fft_rows(spec, grid, 1, phs, out_real=real)
+                else:
+                    tmp = self._tmp('d' if real else 'c', n)
+                    self._fft_rows(spec, tmp, 1, phs, out_real=real)
+                    self._dot_batched(grid, D['DHT_inv_m' + ms], tmp)
 
     # ------------------------------------------------------------------ spectral operators
     def field_poiss_vec(self, fld):

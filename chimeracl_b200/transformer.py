@@ -56,11 +56,10 @@ class Transformer(TransformerMethodsCL):
         self._make_DHT()
 
     def fb_transform(self, scals=[], vects=[], dir=0, mode='full'):
-        for sclr in scals:
-            self.transform_field(sclr, dir=dir, mode=mode)
+        comps = list(scals)
         for vect in vects:
-            for comp in self.Args['vec_comps']:
-                self.transform_field(vect + comp, dir=dir, mode=mode)
+            comps += [vect + comp for comp in self.Args['vec_comps']]
+        self.transform_fields(comps, dir=dir, mode=mode)
 
     def _make_spectral_axes(self):
         spectral_axes(self.Args)

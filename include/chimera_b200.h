@@ -127,12 +127,13 @@ int chb_warp_axis(double* const* fld_host, const int* is_complex_host, int nfld,
  * relativistic Boris push of px, py, pz, g_inv.  eb_host: HOST array of 6*(M+1)
  * device pointers ordered [m][E,B][x,y,z] (grid_methods_cl.py:176-180).
  * factor_push_dev: DataDev['FactorPush']; np_stay_dev: device scalar written by
- * chb_cell_offsets (the reference passes Args['Np_stay'] by value).  Replaces
+ * chb_cell_offsets (the reference passes Args['Np_stay'] by value).  Particles are
+ * visited cell tile by cell tile through cell_offset / sort_indx.  Replaces
  * gather_and_push, kernels/grid_deposit_m0.cl:280-427,
  * kernels/grid_deposit_m1.cl:330-511 (grid_methods_cl.py:168-192). */
 int chb_gather_push(int M, const double* x, const double* y, const double* z, double* px,
                     double* py, double* pz, double* g_inv, const uint32_t* sort_indx,
-                    const double* factor_push_dev, uint32_t np,
+                    const uint32_t* cell_offset, const double* factor_push_dev, uint32_t np,
                     const uint32_t* np_stay_dev, uint32_t Nx, uint32_t Nr,
                     const double* xmin, const double* dx_inv, const double* rmin,
                     const double* dr_inv, const double* const* eb_host, void* stream);
@@ -193,6 +194,13 @@ int chb_dht(const double* A, uint32_t lda, const double* B, uint32_t ldb, double
             uint32_t ldc, uint32_t M, uint32_t K, uint32_t N, int is_complex,
             double alpha_re, double alpha_im, int accumulate, void* stream);
 
+/* C_k = A . B_k for nbatch <= CHB_MAX_FIELDS right-hand sides sharing A, dimensions and
+ * leading dimensions, in one launch (B_host / C_host: HOST arrays of device pointers):
+ * all components of one fb_transform call (transformer.py:17-26). */
+int chb_dht_batched(const double* A, uint32_t lda, const double* const* B_host,
+                    double* const* C_host, int nbatch, uint32_t ldb, uint32_t ldc, uint32_t M,
+                    uint32_t K, uint32_t N, int is_complex, void* stream);
+
 /* Same product written to two outputs, C1 (op1)= a1*A.B and C2 (op2)= a2*A.B (same
  * leading dimension): the "b = dDHT.x; y += a1*b; z += a2*b" pattern of field_grad /
  * field_rot (transformer_methods_cl.py:111-133, :228-263) in one pass. */
@@ -212,6 +220,12 @@ int chb_dht2(const double* A, uint32_t lda, const double* B, uint32_t ldb, doubl
  * Replaces Reikna FFT `_fft`, methods/transformer_methods_cl.py:482-509, plus the
  * cast / phase / slice-copy passes around it (:295-311, :338-358). */
 int chb_fft_max_pow2(void);
+/* The same transform applied to nbatch <= CHB_MAX_FIELDS arrays in one launch. */
+int chb_fft_x_batched(const double* const* in_host, double* const* out_host, int nbatch,
+                      uint32_t rows, uint32_t Nx, size_t in_stride, size_t out_stride,
+                      int inverse, int in_real, int out_real, const double* phase,
+                      int phase_on_input, const double* twiddles, uint32_t L,
+                      const double* chirp, const double* bfft, void* stream);
 int chb_fft_x(const double* in, double* out, uint32_t rows, uint32_t Nx, size_t in_stride,
               size_t out_stride, int inverse, int in_real, int out_real,
               const double* phase, int phase_on_input, const double* twiddles,

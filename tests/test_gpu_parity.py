@@ -3,7 +3,7 @@ API) against the oracle on identical seeded inputs, and against the committed go
 vectors produced from the reference's own kernels.
 
 Tolerances (stated per check): integer products and the coordinate push are
-bit-exact; gather + Boris is bit-exact given identical fields; depositions
+bit-exact; gather + Boris <= 1e-13 given identical fields; depositions
 <= 1e-12 * max|field| (summation order differs); single transforms / spectral
 operators <= 1e-12 relative to max; full steps <= 1e-10.
 """
@@ -177,9 +177,9 @@ def test_deposit_and_gather(comm, M):
     for k in So.D:
         if k[0] in "EB" and "_fb_" not in k:     # ghost rows written by warp_axis
             assert np.array_equal(S.DataDev[k].get(), So.D[k]), k
-    for k in ("px", "py", "pz", "g_inv"):
+    for k in ("px", "py", "pz", "g_inv"):          # FMA-contracted mode sum: few ulp
         got, ref = P.DataDev[k].get(), Po.D[k]
-        assert np.array_equal(got, ref), (k, np.abs(got - ref).max())
+        assert rel_err(got, ref) < 1e-13, (k, np.abs(got - ref).max())
 
 
 def test_deposit_dense_cells(comm):

@@ -1,0 +1,42 @@
+"""Sets up the bench workload (or --small) and runs a few PIC steps; meant to be run
+under ncu on the GPU box:  ncu ... python tools/profile_step.py --steps 2"""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--small", action="store_true")
+    a = ap.parse_args()
+    import torch
+    from chimeracl_b200.methods.generic_methods_cl import Communicator
+    from chimeracl_b200.particles import Particles
+    from chimeracl_b200.solver import Solver
+    from chimeracl_b200.pic_loop import PIC_loop
+    comm = Communicator(answers=[0, 0], seed=1234)
+    solver = Solver(dict(bench.workload(a.small)), comm)
+    ecfg, icfg = bench.species_cfgs(solver.Args)
+    eons, ions = Particles(ecfg, comm), Particles(icfg, comm)
+    eons.make_new_domain(bench.plasma_domain(solver.Args))
+    eons.add_new_particles()
+    ions.add_new_particles(source=eons)
+    eons.free_added()
+    for p in (eons, ions):
+        p.sort_parts(solver)
+        p.align_parts()
+    loop = PIC_loop(solvers=[solver], species=[eons, ions])
+    torch.cuda.synchronize()
+    torch.cuda.profiler.start()
+    for _ in range(a.steps):
+        loop.step()
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
+
+
+if __name__ == "__main__":
+    main()
