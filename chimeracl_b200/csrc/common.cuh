@@ -93,6 +93,15 @@ __device__ __forceinline__ void warp_runs(uint32_t key, bool valid, int lane,
   len = next - head_lane;
 }
 
+// 8-byte asynchronous global -> shared copy (LDGSTS); the copy lands without
+// occupying a register, so many particles' attributes can be in flight per thread.
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
 __device__ __forceinline__ void red_add_f64(double* addr, double v) {
   atomicAdd(addr, v);  // result unused -> RED.E.ADD.F64
 }

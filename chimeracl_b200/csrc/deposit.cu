@@ -8,9 +8,10 @@
 // Design (HBM-bound FP64 scatter-add, not GEMM-shaped):
 //   * one CTA owns kDepCells consecutive cells = one contiguous range of the
 //     cell-sorted particle list (cell_offset), processed in batches;
-//   * phase 1 (thread per particle, coalesced through sort_indx): load the
-//     attributes once, do the expensive per-particle math (sqrt, 1/r, scaled
-//     coordinates) and stage 5-8 doubles per particle in shared memory;
+//   * stage (thread per particle, through sort_indx): the attributes are copied
+//     global->shared ASYNCHRONOUSLY (cp.async, double buffered) while the previous
+//     batch is being accumulated; on arrival the owning thread converts them in
+//     place (sqrt, 1/r, scaled coordinates), once per particle;
 //   * phase 2 (thread per cell and component): accumulate the cell's 2x2 node
 //     stencil for all modes in registers from shared memory (padded layout, no
 //     bank conflicts for ~uniform fillings) -- no atomics at all inside a cell;
@@ -54,13 +55,28 @@ template <bool VEC>
 struct DepShape { static constexpr int kThreads = kDepCells * (VEC ? 3 : 1); };
 
 template <int M, bool VEC>
+struct DepSmem {
+  // staged doubles per particle: raw attributes land here asynchronously and are
+  // converted in place to (ax, ar, wp, [px, py, pz], [e0, e1])
+  static constexpr int kSlots = VEC ? 8 : 5;
+  static constexpr int kBytes = 2 * kSlots * kDepPad * (int)sizeof(double);  // double buffered
+};
+
+template <int M, bool VEC>
 __global__ void __launch_bounds__(DepShape<VEC>::kThreads, VEC ? 3 : 6)
 depose_kernel(DepArgs<M, VEC> a) {
   constexpr int NC = VEC ? 3 : 1;
   constexpr int NT = DepShape<VEC>::kThreads;
   constexpr int MM = M > 0 ? M : 1;
-  constexpr int NSTAGE = 3 + (VEC ? 3 : 0) + (M > 0 ? 2 : 0);
-  __shared__ double stage[NSTAGE][kDepPad];
+  constexpr int NS = DepSmem<M, VEC>::kSlots;
+  constexpr int KP = (kDepBatch + NT - 1) / NT;     // particles loaded per thread and batch
+  // slot layout (VEC):   raw x y z px py pz w g_inv -> ax ar wp px py pz e0 e1
+  // slot layout (!VEC):  raw x y z w  -          -> ax ar wp e0 e1
+  constexpr int SL_E0 = VEC ? 6 : 3, SL_E1 = VEC ? 7 : 4;
+  extern __shared__ double dep_smem[];
+  auto slot = [&](int buf, int sl, int p) -> double& {
+    return dep_smem[(buf * NS + sl) * kDepPad + p];
+  };
 
   const GridVals g = load_geom(a.geom);
   const int Nx_cell = g.Nx - 1;
@@ -90,56 +106,98 @@ depose_kernel(DepArgs<M, VEC> a) {
 #pragma unroll
     for (int n = 0; n < 4; ++n) accm[m][n][0] = accm[m][n][1] = 0.0;
 
-  for (uint32_t b0 = P0; b0 < P1; b0 += kDepBatch) {
-    const uint32_t b1 = min(b0 + (uint32_t)kDepBatch, P1);
-    // ---------------- phase 1: thread per particle (all threads of the CTA)
-    for (uint32_t j = b0 + threadIdx.x; j < b1; j += NT) {
-      const uint32_t s = __ldg(a.sort_indx + j);
-      const double xp = __ldg(a.x + s), yp = __ldg(a.y + s), zp = __ldg(a.z + s);
-      double wp;
-      if (VEC) wp = __dmul_rn(__dmul_rn(__ldg(a.w + s), __ldg(a.g_inv + s)), q);
-      else wp = __dmul_rn(__ldg(a.w + s), q);
-      const double rp = __dsqrt_rn(__dadd_rn(__dmul_rn(yp, yp), __dmul_rn(zp, zp)));
-      const int p = pidx((int)(j - b0));
-      stage[0][p] = __dmul_rn(__dsub_rn(xp, g.xmin), g.dx_inv);
-      stage[1][p] = __dmul_rn(__dsub_rn(rp, g.rmin), g.dr_inv);
-      stage[2][p] = wp;
+  // sorted indices of the particles this thread stages in the NEXT issued batch
+  uint32_t sidx[KP];
+  auto load_sidx = [&](uint32_t b0) {
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+      const uint32_t j = b0 + threadIdx.x + k * NT;
+      sidx[k] = (j < P1 && threadIdx.x + k * NT < kDepBatch) ? __ldg(a.sort_indx + j) : 0xffffffffu;
+    }
+  };
+  // asynchronous stage of batch [b0, b0+kDepBatch) into buffer `buf`
+  auto issue = [&](uint32_t b0, int buf) {
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+      const uint32_t s = sidx[k];
+      if (s == 0xffffffffu) continue;
+      const int p = pidx((int)(threadIdx.x + k * NT));
+      cp_async8(&slot(buf, 0, p), a.x + s);
+      cp_async8(&slot(buf, 1, p), a.y + s);
+      cp_async8(&slot(buf, 2, p), a.z + s);
       if (VEC) {
-        stage[3][p] = __ldg(a.px + s);
-        stage[4][p] = __ldg(a.py + s);
-        stage[5][p] = __ldg(a.pz + s);
+        cp_async8(&slot(buf, 3, p), a.px + s);
+        cp_async8(&slot(buf, 4, p), a.py + s);
+        cp_async8(&slot(buf, 5, p), a.pz + s);
+        cp_async8(&slot(buf, 6, p), a.w + s);
+        cp_async8(&slot(buf, 7, p), a.g_inv + s);
+      } else {
+        cp_async8(&slot(buf, 3, p), a.w + s);
       }
+    }
+    cp_async_commit();
+  };
+  // in-place raw -> derived conversion of the particles this thread staged
+  auto convert = [&](uint32_t b0, int buf) {
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+      const uint32_t j = b0 + threadIdx.x + k * NT;
+      if (!(j < P1 && threadIdx.x + k * NT < kDepBatch)) continue;
+      const int p = pidx((int)(threadIdx.x + k * NT));
+      const double xp = slot(buf, 0, p), yp = slot(buf, 1, p), zp = slot(buf, 2, p);
+      double wp;
+      if (VEC) wp = __dmul_rn(__dmul_rn(slot(buf, 6, p), slot(buf, 7, p)), q);
+      else wp = __dmul_rn(slot(buf, 3, p), q);
+      const double rp = __dsqrt_rn(__dadd_rn(__dmul_rn(yp, yp), __dmul_rn(zp, zp)));
+      slot(buf, 0, p) = __dmul_rn(__dsub_rn(xp, g.xmin), g.dx_inv);
+      slot(buf, 1, p) = __dmul_rn(__dsub_rn(rp, g.rmin), g.dr_inv);
+      slot(buf, 2, p) = wp;
       if (M > 0) {
         // depose_scalar uses the unguarded 1/r (grid_deposit_m1.cl:115),
         // depose_vector guards it (grid_deposit_m1.cl:280-281)
-        double rinv = (VEC && !(rp > 0.0)) ? 0.0 : __drcp_rn(rp);
-        stage[NSTAGE - 2][p] = __dmul_rn(yp, rinv);
-        stage[NSTAGE - 1][p] = __dmul_rn(zp, rinv);
+        const double rinv = (VEC && !(rp > 0.0)) ? 0.0 : __drcp_rn(rp);
+        slot(buf, SL_E0, p) = __dmul_rn(yp, rinv);
+        slot(buf, SL_E1, p) = __dmul_rn(zp, rinv);
       }
     }
-    __syncthreads();
-    // ---------------- phase 2: thread per (cell, component)
+  };
+
+  load_sidx(P0);
+  issue(P0, 0);
+  if (P0 + kDepBatch < P1) load_sidx(P0 + kDepBatch);
+
+  int buf = 0;
+  for (uint32_t b0 = P0; b0 < P1; b0 += kDepBatch, buf ^= 1) {
+    const uint32_t b1 = min(b0 + (uint32_t)kDepBatch, P1);
+    cp_async_wait_all();          // this thread's copies of batch b0 have landed
+    convert(b0, buf);
+    __syncthreads();              // batch b0 ready for everyone; batch b0-1 fully consumed
+    if (b1 < P1) {                // overlap: stage the next batch while accumulating this one
+      issue(b1, buf ^ 1);
+      if (b1 + kDepBatch < P1) load_sidx(b1 + kDepBatch);
+    }
+    // ---------------- accumulate: thread per (cell, component)
     const uint32_t js = max(S, b0), je = min(E, b1);
     for (uint32_t j = js; j < je; ++j) {
       const int p = pidx((int)(j - b0));
-      const double wp = stage[2][p];
-      double sX1 = __dsub_rn(stage[0][p], dix);
+      const double wp = slot(buf, 2, p);
+      double sX1 = __dsub_rn(slot(buf, 0, p), dix);
       double sX0 = __dsub_rn(1.0, sX1);
-      const double sR1 = __dsub_rn(stage[1][p], dir_);
+      const double sR1 = __dsub_rn(slot(buf, 1, p), dir_);
       const double sR0 = __dsub_rn(1.0, sR1);
       sX0 = __dmul_rn(sX0, wp);
       sX1 = __dmul_rn(sX1, wp);
-      const double jk = VEC ? stage[3 + comp][p] : 1.0;
       double pj[4] = {__dmul_rn(sR0, sX0), __dmul_rn(sR0, sX1),
                       __dmul_rn(sR1, sX0), __dmul_rn(sR1, sX1)};
       if (VEC) {
+        const double jk = slot(buf, 3 + comp, p);
 #pragma unroll
         for (int n = 0; n < 4; ++n) pj[n] = __dmul_rn(pj[n], jk);
       }
       double er[MM], ei[MM];
       if (M > 0) {
-        er[0] = stage[NSTAGE - 2][p];
-        ei[0] = stage[NSTAGE - 1][p];
+        er[0] = slot(buf, SL_E0, p);
+        ei[0] = slot(buf, SL_E1, p);
 #pragma unroll
         for (int m = 1; m < MM; ++m) {  // e^{i(m+1)theta}
           er[m] = er[m - 1] * er[0] - ei[m - 1] * ei[0];
@@ -158,7 +216,6 @@ depose_kernel(DepArgs<M, VEC> a) {
         }
       }
     }
-    __syncthreads();
   }
 
   // ---------------- flush: one RED per node value per cell
@@ -182,7 +239,11 @@ depose_kernel(DepArgs<M, VEC> a) {
 template <int M, bool VEC>
 static int launch_depose(DepArgs<M, VEC>& a, cudaStream_t st) {
   uint32_t grid = (a.ncells + kDepCells - 1) / kDepCells;
-  depose_kernel<M, VEC><<<grid, DepShape<VEC>::kThreads, 0, st>>>(a);
+  constexpr int smem = DepSmem<M, VEC>::kBytes;
+  cudaError_t e = cudaFuncSetAttribute(depose_kernel<M, VEC>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return (int)e;
+  depose_kernel<M, VEC><<<grid, DepShape<VEC>::kThreads, smem, st>>>(a);
   CHB_RETURN_LAST_ERROR();
 }
 

@@ -45,12 +45,28 @@ struct GatherArgs {
   uint32_t tiles_per_row;
 };
 
+constexpr int kGatSlots = 4;   // particles in flight per thread (async landing zone)
+
+template <int M>
+struct GatSmem {
+  static constexpr int kMM = M > 0 ? M : 1;
+  static constexpr int kStencilM = M > 0 ? M * 6 * 2 * kGatCols * 2 : 0;   // doubles
+  static constexpr int kStencil0 = 6 * 2 * kGatCols;                       // doubles
+  static constexpr int kLanding = 6 * kGatSlots * kGatThreads;             // doubles
+  static constexpr int kBytes = (kStencilM + kStencil0 + kLanding) * (int)sizeof(double);
+};
+
 template <int M>
 __global__ void __launch_bounds__(kGatThreads, 3)
 gather_push_kernel(GatherArgs<M> a) {
-  // node planes: [field 0..5][row 0..1][col], real for m=0, complex for m>=1
-  __shared__ double s0[6][2][kGatCols];
-  __shared__ double2 sm[M > 0 ? M : 1][6][2][kGatCols];
+  // node planes: [field 0..5][row 0..1][col], complex for m>=1 (first, 16-byte
+  // aligned), real for m=0; then the landing zone [attr 0..5][slot][thread]
+  extern __shared__ double2 gat_smem[];
+  typedef double2 (*SmT)[6][2][kGatCols];
+  typedef double (*S0T)[2][kGatCols];
+  SmT sm = reinterpret_cast<SmT>(gat_smem);
+  S0T s0 = reinterpret_cast<S0T>(reinterpret_cast<double*>(gat_smem) + GatSmem<M>::kStencilM);
+  double* land = reinterpret_cast<double*>(gat_smem) + GatSmem<M>::kStencilM + GatSmem<M>::kStencil0;
 
   const GridVals g = load_geom(a.geom);
   const int Nx_cell = g.Nx - 1, Nr_cell = g.Nr - 1;
@@ -60,6 +76,31 @@ gather_push_kernel(GatherArgs<M> a) {
   const uint32_t c0 = (uint32_t)ir_t * (uint32_t)Nx_cell + (uint32_t)ix0;
   const uint32_t P0 = a.cell_offset[c0], P1 = a.cell_offset[c0 + ncell];
   if (P0 == P1) return;
+
+  const uint32_t np_stay = __ldg(a.np_stay);
+  const double dt_2 = 0.5 * __ldg(a.factor_push);
+
+  // Particles of the tile in rounds of kGatSlots*kGatThreads: every thread first
+  // issues the asynchronous copies of ALL its particles of the round (6 attributes
+  // x kGatSlots in flight per thread, no registers held), then consumes them.
+  // A thread only ever reads the slots it filled itself, so no barrier is needed.
+  auto issue_round = [&](uint32_t base) {
+#pragma unroll
+    for (int k = 0; k < kGatSlots; ++k) {
+      const uint32_t ip = base + threadIdx.x + k * kGatThreads;
+      const uint32_t s = ip < P1 ? __ldg(a.sort_indx + ip) : 0xffffffffu;
+      if (s >= np_stay) continue;   // also skips the padding
+      double* l = land + k * kGatThreads + threadIdx.x;
+      cp_async8(l + 0 * kGatSlots * kGatThreads, a.x + s);
+      cp_async8(l + 1 * kGatSlots * kGatThreads, a.y + s);
+      cp_async8(l + 2 * kGatSlots * kGatThreads, a.z + s);
+      cp_async8(l + 3 * kGatSlots * kGatThreads, a.px + s);
+      cp_async8(l + 4 * kGatSlots * kGatThreads, a.py + s);
+      cp_async8(l + 5 * kGatSlots * kGatThreads, a.pz + s);
+    }
+    cp_async_commit();
+  };
+  issue_round(P0);   // particle data starts flowing while the stencil is staged
 
   // ---- stage the node stencil (rows ir_t, ir_t+1; columns ix0 .. ix0+ncell)
   const int ncol = min(ncell + 1, g.Nx - ix0);
@@ -77,14 +118,20 @@ gather_push_kernel(GatherArgs<M> a) {
   }
   __syncthreads();
 
-  const uint32_t np_stay = __ldg(a.np_stay);
-  const double dt_2 = 0.5 * __ldg(a.factor_push);
 
-  for (uint32_t ip = P0 + threadIdx.x; ip < P1; ip += kGatThreads) {
-    const uint32_t s = __ldg(a.sort_indx + ip);
+  for (uint32_t base = P0; base < P1; base += kGatSlots * kGatThreads) {
+    if (base != P0) issue_round(base);
+    cp_async_wait_all();
+#pragma unroll 1
+    for (int k = 0; k < kGatSlots; ++k) {
+    const uint32_t ip = base + threadIdx.x + k * kGatThreads;
+    if (ip >= P1) break;
+    const uint32_t s = __ldg(a.sort_indx + ip);   // L1 hit (read by issue_round)
     if (s >= np_stay) continue;  // gate on the STORAGE index (grid_deposit_m1.cl:367-368)
-    const double xp = __ldg(a.x + s), yp = __ldg(a.y + s), zp = __ldg(a.z + s);
-    double u_p[3] = {a.px[s], a.py[s], a.pz[s]};
+    const double* l = land + k * kGatThreads + threadIdx.x;
+    const double xp = l[0], yp = l[1 * kGatSlots * kGatThreads], zp = l[2 * kGatSlots * kGatThreads];
+    double u_p[3] = {l[3 * kGatSlots * kGatThreads], l[4 * kGatSlots * kGatThreads],
+                     l[5 * kGatSlots * kGatThreads]};
     double rp;
     int ix, ir;
     cell_coords(xp, yp, zp, g, rp, ix, ir);
@@ -188,6 +235,7 @@ gather_push_kernel(GatherArgs<M> a) {
     a.py[s] = u_p[1];
     a.pz[s] = u_p[2];
     a.g_inv[s] = g_p_inv;
+    }
   }
 }
 
@@ -202,7 +250,11 @@ static int launch_gather(const double* x, const double* y, const double* z, doub
   for (int k = 0; k < 6 * (M + 1); ++k) a.eb[k] = eb[k];
   a.tiles_per_row = (g.Nx - 1 + kGatCells - 1) / kGatCells;
   uint32_t grid = a.tiles_per_row * (g.Nr - 1);
-  gather_push_kernel<M><<<grid, kGatThreads, 0, st>>>(a);
+  constexpr int smem = GatSmem<M>::kBytes;
+  cudaError_t e = cudaFuncSetAttribute(gather_push_kernel<M>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return (int)e;
+  gather_push_kernel<M><<<grid, kGatThreads, smem, st>>>(a);
   CHB_RETURN_LAST_ERROR();
 }
 

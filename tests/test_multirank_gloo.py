@@ -1,0 +1,78 @@
+"""world_size-2 test of the N>1 path on CPU (gloo): particles are sharded
+contiguous-by-index over the ranks, every rank deposits its shard on the full grid
+(here with the oracle as the per-rank depositor -- the GPU kernel is covered by the
+-m gpu tests), the raw rho/J arrays are summed with chimeracl_b200.parallel.
+allreduce_sum and only then post-processed.  The result must equal the
+single-process deposit of all particles."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import orchestration as O
+from oracle.np_kernels import NumpyKernels
+
+from helpers import load_golden, oracle_case_from_golden, rel_err
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world))
+    from chimeracl_b200.parallel import allreduce_sum, init_distributed, shard_range
+    pg = init_distributed(backend="gloo")
+    M = 1
+    K = NumpyKernels(M)
+    G = load_golden(M)
+    S, P, I = oracle_case_from_golden(G, K)
+    lo, hi = shard_range(P.Args["Np"], rank, world)
+    for p in (P, I):                       # this rank's shard of every species
+        p.set_particles(**{a: p.D[a][lo:hi] for a in p.attrs})
+        p.push_coords("half")              # electrons move off the ions: rho != 0
+        p.sort_parts(S)
+    names = ["rho"] + ["J" + c for c in "xyz"]
+    arrays = [S.D["%s_m%d" % (n, m)] for n in names for m in range(M + 1)]
+    for a in arrays:
+        a[...] = 0
+    flds_j = [S.D["J%s_m%d" % (c, m)] for m in range(M + 1) for c in "xyz"]
+    flds_r = [S.D["rho_m%d" % m] for m in range(M + 1)]
+    D = P.D
+    K.depose_vector(D["sort_indx"], D["x"], D["y"], D["z"], D["px"], D["py"], D["pz"],
+                    D["g_inv"], D["w"], D["cell_offset"], -1, S.Args, flds_j)
+    for p, q in ((P, -1), (I, 1)):
+        D = p.D
+        K.depose_scalar(D["sort_indx"], D["x"], D["y"], D["z"], D["w"], D["cell_offset"], q,
+                        S.Args, flds_r)
+    tensors = [torch.from_numpy(a) for a in arrays]   # share memory with the arrays
+    allreduce_sum(tensors, pg)
+    for n in names:
+        S.postproc_depose(n)
+    if rank == 0:
+        np.savez(os.path.join(out_dir, "dist.npz"),
+                 **{"%s_m%d" % (n, m): S.D["%s_m%d" % (n, m)] for n in names for m in range(M + 1)})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_deposit_allreduce_equals_single_process(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    got = np.load(tmp_path / "dist.npz")
+    M = 1
+    K = NumpyKernels(M)
+    S, P, I = oracle_case_from_golden(load_golden(M), K)
+    for p in (P, I):
+        p.push_coords("half")
+        p.sort_parts(S)
+    S.depose_currents([P, I])
+    S.depose_charge([P, I])
+    for k in got.files:
+        assert rel_err(got[k], S.D[k]) < 1e-13, k
