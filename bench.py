@@ -220,7 +220,7 @@ def run_reference(args, as_baseline=False):
             "cpu_baseline": cpu,
             "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def bench_config(A, np_per_gpu, n_gpus):
@@ -382,6 +382,9 @@ def run_ours(args):
     ms_e2e = timed(e2e_step, ne2e)
     e2e_value = np_gpu * world * ne2e / (ms_e2e * 1e-3)
 
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     cpu = None
@@ -406,10 +409,22 @@ def run_ours(args):
                               "hbm_gbs_algorithmic": particle_roof,
                               "frac_of_hbm_peak": particle_roof / peaks["hbm_gbs"]},
             "phases_ms": phases, "kernels": kernels, "kernel_rooflines": rooflines}
-    print(json.dumps(line))
+    emit(line)
+
+
+def emit(line):
+    """Exactly one JSON line on the real stdout (libraries may print to fd 1)."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)          # anything else written to stdout goes to stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

@@ -127,6 +127,7 @@ struct FftArgs {
   const double2* phase;  // Nx entries or nullptr
   const double2* chirp;  // Bluestein: exp(-i pi n^2 / N), n < N
   const double2* bfft;   // Bluestein: FFT_L(b)/L
+  const double* filter;  // optional real (rows x Nx) factor on the output (spectral smoothing)
   int N;
   int inverse;           // normalised inverse transform
   int in_real, out_real; // element types
@@ -145,6 +146,10 @@ __device__ __forceinline__ void store_out(const FftArgs& a, double* row, int ix,
   if (a.inverse) v = cconj(v);
   v.x *= a.scale; v.y *= a.scale;
   if (a.phase_out) v = cmulf(v, __ldg(a.phase + ix));
+  if (a.filter) {
+    const double f = __ldg(a.filter + (size_t)blockIdx.x * a.N + ix);
+    v.x = f * v.x; v.y = f * v.y;
+  }
   if (a.out_real) row[ix] = v.x;
   else reinterpret_cast<double2*>(row)[ix] = v;
 }
@@ -223,7 +228,8 @@ int chb_fft_x_batched(const double* const* in_host, double* const* out_host, int
                       uint32_t rows, uint32_t Nx, size_t in_stride, size_t out_stride,
                       int inverse, int in_real, int out_real, const double* phase,
                       int phase_on_input, const double* twiddles, uint32_t L,
-                      const double* chirp, const double* bfft, void* stream) {
+                      const double* chirp, const double* bfft, const double* out_filter,
+                      void* stream) {
   if (rows == 0 || Nx == 0 || nbatch == 0) return CHB_OK;
   if (nbatch < 0 || nbatch > CHB_MAX_FIELDS) return CHB_ERR_ARG;
   if (L < 8 || (L & (L - 1)) || L > 8192) return CHB_ERR_ARG;
@@ -239,6 +245,7 @@ int chb_fft_x_batched(const double* const* in_host, double* const* out_host, int
   a.phase = (const double2*)phase;
   a.chirp = (const double2*)chirp;
   a.bfft = (const double2*)bfft;
+  a.filter = out_filter;
   a.N = (int)Nx;
   a.inverse = inverse;
   a.in_real = in_real; a.out_real = out_real;
@@ -269,7 +276,8 @@ int chb_fft_x(const double* in, double* out, uint32_t rows, uint32_t Nx, size_t 
               const double* phase, int phase_on_input, const double* twiddles,
               uint32_t L, const double* chirp, const double* bfft, void* stream) {
   return chb_fft_x_batched(&in, &out, 1, rows, Nx, in_stride, out_stride, inverse, in_real,
-                           out_real, phase, phase_on_input, twiddles, L, chirp, bfft, stream);
+                           out_real, phase, phase_on_input, twiddles, L, chirp, bfft, nullptr,
+                           stream);
 }
 
 }  // extern "C"

@@ -90,6 +90,26 @@ __global__ void get_m1_kernel(double2* __restrict__ dst, const double2* __restri
     dst[i] = make_double2(-v.x, v.y);
   }
 }
+// out (op)= alpha*b(ix) + beta*conj(b((Nx-ix) mod Nx)), row by row.  With the m=-1
+// spectrum F_{-1}(kx) = -conj(F_1(-kx)) (get_m1 above) and a REAL operator matrix D,
+// D.F_{-1} = -conj(mirror(D.F_1)): the m=0 "minus" terms of field_grad / field_rot
+// follow from the "plus" product without a second contraction.
+__global__ void mirror_axpy_kernel(double2* __restrict__ out, const double2* __restrict__ b,
+                                   double2 alpha, double2 beta, int accumulate, size_t n,
+                                   uint32_t Nx) {
+  CHB_GRID_STRIDE(i, n) {
+    size_t ir = i / Nx;
+    uint32_t ix = (uint32_t)(i - ir * Nx);
+    uint32_t ixo = ix == 0 ? 0u : Nx - ix;
+    const double2 v = b[i];
+    double2 w = b[ir * Nx + ixo];
+    w.y = -w.y;
+    double2 r = make_double2(alpha.x * v.x - alpha.y * v.y + beta.x * w.x - beta.y * w.y,
+                             alpha.x * v.y + alpha.y * v.x + beta.x * w.y + beta.y * w.x);
+    if (accumulate) { const double2 o = out[i]; r.x += o.x; r.y += o.y; }
+    out[i] = r;
+  }
+}
 // transformer_generic.cl:28-55: exp(sign * i * x0 * kx)
 __global__ void phase_kernel(double2* __restrict__ phs, const double* __restrict__ kx, double x0,
                              double sign, uint32_t Nx) {
@@ -233,6 +253,14 @@ int chb_ab_dot_x(double a_re, double a_im, const double* b, const double* x, dou
 int chb_get_m1(double* dst, const double* src, size_t n, uint32_t Nx, void* stream) {
   if (!n) return CHB_OK;
   get_m1_kernel<<<ew_grid(n), kEB, 0, CHB_ST>>>((double2*)dst, (const double2*)src, n, Nx);
+  CHB_RETURN_LAST_ERROR();
+}
+int chb_mirror_axpy(double* out, const double* b, double a_re, double a_im, double b_re,
+                    double b_im, int accumulate, size_t n, uint32_t Nx, void* stream) {
+  if (!n) return CHB_OK;
+  mirror_axpy_kernel<<<ew_grid(n), kEB, 0, CHB_ST>>>((double2*)out, (const double2*)b,
+                                                     make_double2(a_re, a_im),
+                                                     make_double2(b_re, b_im), accumulate, n, Nx);
   CHB_RETURN_LAST_ERROR();
 }
 int chb_get_phase(double* phs, const double* kx, double x0, int dir, uint32_t Nx, void* stream) {

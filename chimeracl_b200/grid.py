@@ -45,17 +45,14 @@ class Grid(GridMethodsCL):
         self.send_args_to_dev()
 
     def depose_charge(self, species=[]):
-        for m in range(self.Args['M'] + 1):
-            self.set_to(self.DataDev['rho_m' + str(m)], 0)
+        self._flat['rho'].zero_()
         for parts in species:
             self.depose_scalar(parts, 'w', 'rho', charge=parts.Args['charge'])
         self.postproc_depose_scalar('rho')
 
     def depose_currents(self, species=[]):
         comps = self.Args['vec_comps']
-        for m in range(self.Args['M'] + 1):
-            for comp in comps:
-                self.set_to(self.DataDev['J' + comp + '_m' + str(m)], 0)
+        self._flat['J'].zero_()
         for parts in species:
             if 'Immobile' in parts.Args.keys():
                 continue
@@ -75,11 +72,37 @@ class Grid(GridMethodsCL):
         self.Args = grid_geometry(ArgsDict(configs_in))
 
     def _init_grid_data_on_dev(self):
-        names = [f + comp for f in ('E', 'B', 'J', 'G') for comp in self.Args['vec_comps']]
-        names.append('rho')
+        comps = self.Args['vec_comps']
         shape = (self.Args['Nr'], self.Args['Nx'])
-        for name in names:
+        for name in [f + comp for f in ('E', 'B', 'G') for comp in comps]:
             self.DataDev[name + '_m0'] = self.dev_arr(val=0, dtype=np.double, shape=shape)
             for m in range(1, self.Args['M'] + 1):
                 self.DataDev[name + '_m' + str(m)] = self.dev_arr(val=0, dtype=np.complex128,
                                                                  shape=shape)
+        # The deposited fields of one group (J: 3 comps x modes, rho: modes) are views
+        # of ONE flat buffer each, so that the multi-GPU sum over ranks is a single
+        # in-place all-reduce and the zero-fill a single memset.
+        self._flat = {}
+        for group, names in (('J', ['J' + comp for comp in comps]), ('rho', ['rho'])):
+            self._flat[group] = self._alloc_group(names, shape)
+
+    def _alloc_group(self, names, shape):
+        import torch
+        from .devarray import DevArray
+        n = shape[0] * shape[1]
+        n_pad = (n + 1) // 2 * 2                       # keep complex views 16-byte aligned
+        sizes = []
+        for name in names:
+            for m in range(self.Args['M'] + 1):
+                sizes.append((name + '_m' + str(m), n_pad if m == 0 else 2 * n_pad, m > 0))
+        flat = torch.zeros(sum(sz for _, sz, _ in sizes), dtype=torch.float64,
+                           device=self.comm.device)
+        off = 0
+        for key, sz, cplx in sizes:
+            if cplx:
+                view = torch.view_as_complex(flat[off:off + 2 * n].view(n, 2)).view(shape)
+            else:
+                view = flat[off:off + n].view(shape)
+            self.DataDev[key] = DevArray(view)
+            off += sz
+        return flat

@@ -59,18 +59,23 @@ class GridMethodsCL(GenericMethodsCL):
                    P[factors[0]].ptr, P[factors[1]].ptr, P['cell_offset'].ptr,
                    int(np.int8(charge)), *self._geom(), _lib.ptr_array(flds))
 
-    def _allreduce(self, arrays):
+    def _allreduce(self, group, arrays):
         pg = getattr(self.comm, 'process_group', None)
         if pg is None:
             return
         from ..parallel import allreduce_sum
-        allreduce_sum([a.t for a in arrays], pg)
+        flat = getattr(self, '_flat', {}).get(group)
+        if flat is not None:
+            allreduce_sum([flat], pg)          # in place, one collective
+        else:
+            allreduce_sum([a.t for a in arrays], pg)
 
     def _postproc(self, names):
         arrays = []
         for name in names:
             arrays += self._mode_fields(name)
-        self._allreduce(arrays)
+        self._allreduce('rho' if names == ['rho'] else ('J' if names[0][0] == 'J' else None),
+                        arrays)
         ptrs = _lib.ptr_array([a.ptr for a in arrays])
         flags = _lib.int_array([1 if a.dtype == np.complex128 else 0 for a in arrays])
         self._call('chb_postproc_depose', ptrs, flags, len(arrays), int(self.Args['Nx']),

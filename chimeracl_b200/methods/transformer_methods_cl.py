@@ -67,7 +67,8 @@ class TransformerMethodsCL(GenericMethodsCL):
         self._fft_chirp = DevArray.from_numpy(chirp, dev) if chirp is not None else None
         self._fft_bfft = DevArray.from_numpy(bfft, dev) if bfft is not None else None
 
-    def _fft_rows(self, src, dst, direction, phase=None, in_real=False, out_real=False):
+    def _fft_rows(self, src, dst, direction, phase=None, in_real=False, out_real=False,
+                  out_filter=None):
         """dst = FFT_x(src) row by row; src/dst are 2-D DevArrays (views allowed) or
         equally long lists of them (one batched launch)."""
         srcs = src if isinstance(src, (list, tuple)) else [src]
@@ -82,7 +83,8 @@ class TransformerMethodsCL(GenericMethodsCL):
                        phase.ptr if phase is not None else None,
                        1 if direction == 1 else 0, self._fft_tw.ptr, self._fft_L,
                        self._fft_chirp.ptr if self._fft_chirp is not None else None,
-                       self._fft_bfft.ptr if self._fft_bfft is not None else None)
+                       self._fft_bfft.ptr if self._fft_bfft is not None else None,
+                       out_filter.ptr if out_filter is not None else None)
 
     def _fft(self, arr_out, arr, dir):
         """Plain FFT along axis 1 (numpy conventions, normalised inverse): the
@@ -155,11 +157,13 @@ class TransformerMethodsCL(GenericMethodsCL):
     def transform_field(self, arg_cmp, dir, mode):
         self.transform_fields([arg_cmp], dir, mode)
 
-    def transform_fields(self, comps, dir, mode):
+    def transform_fields(self, comps, dir, mode, smooth=False):
         """Forward (dir=0) / backward (dir=1) Fourier-Bessel transform of several
         components at once: per azimuthal mode one batched DHT and one batched FFT
         launch (mode='half': FFT only).  Same arithmetic per component as
-        reference transformer_methods_cl.py:290-455."""
+        reference transformer_methods_cl.py:290-455.  smooth=True (forward only) also
+        applies SmoothingFilter_m to the result, i.e. the fields_smooth() call that
+        follows the forward transform in pic_loop.py:99-103, without an extra pass."""
         if not comps:
             return
         D = self.DataDev
@@ -172,15 +176,16 @@ class TransformerMethodsCL(GenericMethodsCL):
             grid = [D[c + '_m' + ms][1:] for c in comps]
             spec = [D[c + '_fb_m' + ms] for c in comps]
             if dir == 0:
+                flt = D['SmoothingFilter_m' + ms] if smooth else None
                 if not full:
-                    self._fft_rows(grid, spec, 0, phs, in_real=real)
+                    self._fft_rows(grid, spec, 0, phs, in_real=real, out_filter=flt)
                 elif real:
                     tmp = self._tmp('d', n)
                     self._dot_batched(tmp, D['DHT_m0'], grid)
-                    self._fft_rows(tmp, spec, 0, phs, in_real=True)
+                    self._fft_rows(tmp, spec, 0, phs, in_real=True, out_filter=flt)
                 else:
                     self._dot_batched(spec, D['DHT_m' + ms], grid)
-                    self._fft_rows(spec, spec, 0, phs)          # in place
+                    self._fft_rows(spec, spec, 0, phs, out_filter=flt)   # in place
             else:
                 if not full:
                     self._fft_rows(spec, grid, 1, phs, out_real=real)
@@ -207,12 +212,37 @@ class TransformerMethodsCL(GenericMethodsCL):
                 self.mult_elementwise(self.DataDev['SmoothingFilter_m' + str(m)],
                                       self.DataDev[fld + '_fb_m' + str(m)])
 
+    def _mirror_axpy(self, out, b, alpha, beta, accumulate):
+        alpha, beta = complex(alpha), complex(beta)
+        self._call('chb_mirror_axpy', out.ptr, b.ptr, alpha.real, alpha.imag, beta.real,
+                   beta.imag, int(accumulate), b.size, int(self.Args['Nx']))
+
+    def _m0_pm_identical(self):
+        """dDHT_minus_m0 == dDHT_plus_m0 (jn_zeros(-1, n) == jn_zeros(1, n)): then
+        D.F_{-1} = -conj(mirror(D.F_{+1})) and the m=0 'minus' contractions are free."""
+        flag = self.__dict__.get('_m0_pm_flag')
+        if flag is None:
+            D = self.DataDev
+            flag = bool(self.Args['M'] > 0 and
+                        np.array_equal(D['dDHT_minus_m0'].get(), D['dDHT_plus_m0'].get()))
+            self._m0_pm_flag = flag
+        return flag
+
     def field_grad(self, scl_in, vec_out):
         D, M = self.DataDev, self.Args['M']
-        self._get_mm1_scl(scl_in)
+        fast0 = self._m0_pm_identical()
+        if not fast0:
+            self._get_mm1_scl(scl_in)
         for m in range(M + 1):
             ox, oy, oz = (D[vec_out + c + '_fb_m' + str(m)] for c in 'xyz')
             self.ab_dot_x(1.j, D['kx'], D[scl_in + '_fb_m' + str(m)], ox)
+            if m == 0 and fast0:
+                # b+ = dDHT+ . scl_1 ; b- = dDHT- . scl_{-1} = -conj(mirror(b+))
+                bp = D['fld_buff0_c']
+                self._dot(bp, D['dDHT_plus_m0'], D[scl_in + '_fb_m1'])
+                self._mirror_axpy(oy, bp, 1., 1., False)       # oy = -b- + b+
+                self._mirror_axpy(oz, bp, -1.j, 1.j, False)    # oz = -i b- - i b+
+                continue
             if m > 0:
                 src = D[scl_in + '_fb_m' + str(m - 1)]
             elif M > 0:
@@ -250,11 +280,25 @@ class TransformerMethodsCL(GenericMethodsCL):
 
     def field_rot(self, fld_in, fld_out):
         D, M = self.DataDev, self.Args['M']
-        self._get_mm1_vec(fld_in)
+        fast0 = self._m0_pm_identical()
+        if not fast0:
+            self._get_mm1_vec(fld_in)
         for m in range(M + 1):
             ox, oy, oz = (D[fld_out + c + '_fb_m' + str(m)] for c in 'xyz')
             self.ab_dot_x(-1.j, D['kx'], D[fld_in + 'z' + '_fb_m' + str(m)], oy)
             self.ab_dot_x(1.j, D['kx'], D[fld_in + 'y' + '_fb_m' + str(m)], oz)
+            if m == 0 and fast0:
+                fx, fy, fz = (D[fld_in + c + '_fb_m1'] for c in 'xyz')
+                dp = D['dDHT_plus_m0']
+                # X+ = dDHT+.(fz + i fy); the m-1 term is conj(mirror(X+))
+                self.axpbyz(1, fz, 1.j, fy, D['fld_buff0_c'])
+                self._dot(D['fld_buff1_c'], dp, D['fld_buff0_c'])
+                self._mirror_axpy(ox, D['fld_buff1_c'], 1., 1., False)
+                # b' = dDHT+.fx ; b = dDHT-.fx_{-1} = -conj(mirror(b'))
+                self._dot(D['fld_buff0_c'], dp, fx)
+                self._mirror_axpy(oy, D['fld_buff0_c'], -1.j, 1.j, True)   # oy -= i b + i b'
+                self._mirror_axpy(oz, D['fld_buff0_c'], -1., -1., True)    # oz += b - b'
+                continue
             if m > 0:
                 fx, fy, fz = (D[fld_in + c + '_fb_m' + str(m - 1)] for c in 'xyz')
             elif M > 0:

@@ -43,6 +43,9 @@ def allreduce_sum(tensors, group=None):
         return
     if dist.get_world_size(group) == 1:
         return
+    if len(tensors) == 1 and tensors[0].is_contiguous() and not tensors[0].is_complex():
+        dist.all_reduce(tensors[0], op=dist.ReduceOp.SUM, group=group)   # in place
+        return
     views = [torch.view_as_real(t).reshape(-1) if t.is_complex() else t.reshape(-1)
              for t in tensors]
     flat = torch.cat(views)

@@ -75,13 +75,11 @@ class PIC_loop:
             solver.depose_charge(species=self.species)
             self.timer_record('depose')
 
+            # forward transform with the spectral smoothing (reference: a separate
+            # fields_smooth(['rho','Jx','Jy','Jz']) pass) folded into its last stage
             self.timer_start()
-            solver.fb_transform(scals=['rho', ], vects=['J', ], dir=0)
+            solver.fb_transform(scals=['rho', ], vects=['J', ], dir=0, smooth=True)
             self.timer_record('transform')
-
-            self.timer_start()
-            solver.fields_smooth(flds=['rho', 'Jx', 'Jy', 'Jz'])
-            self.timer_record('smooth')
 
             self.timer_start()
             for m in range(0, solver.Args['M'] + 1):

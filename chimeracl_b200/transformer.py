@@ -55,11 +55,11 @@ class Transformer(TransformerMethodsCL):
         self._make_spectral_axes()
         self._make_DHT()
 
-    def fb_transform(self, scals=[], vects=[], dir=0, mode='full'):
+    def fb_transform(self, scals=[], vects=[], dir=0, mode='full', smooth=False):
         comps = list(scals)
         for vect in vects:
             comps += [vect + comp for comp in self.Args['vec_comps']]
-        self.transform_fields(comps, dir=dir, mode=mode)
+        self.transform_fields(comps, dir=dir, mode=mode, smooth=smooth)
 
     def _make_spectral_axes(self):
         spectral_axes(self.Args)

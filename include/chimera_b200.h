@@ -163,6 +163,12 @@ int chb_ab_dot_x(double a_re, double a_im, const double* b, const double* x, dou
 /* dst(ix) = -conj(src((Nx-ix) mod Nx)) per row: the m=-1 spectrum.
  * kernels/transformer_generic.cl:3-24 (transformer_methods_cl.py:265-288). */
 int chb_get_m1(double* dst, const double* src, size_t n, uint32_t Nx, void* stream);
+/* out (op)= alpha*b(ix) + beta*conj(b((Nx-ix) mod Nx)) per row (op: '=' or '+=').
+ * Expresses the m=0 "m-1" terms of field_grad / field_rot
+ * (transformer_methods_cl.py:104-121, :208-235) through the "m+1" product, using
+ * F_{-1} = -conj(mirror F_1) (get_m1) and dDHT_minus_m0 == dDHT_plus_m0. */
+int chb_mirror_axpy(double* out, const double* b, double a_re, double a_im, double b_re,
+                    double b_im, int accumulate, size_t n, uint32_t Nx, void* stream);
 /* phs[ix] = exp(+i*x0*kx[ix]) (dir=1) or exp(-i*x0*kx[ix]) (dir=0).
  * kernels/transformer_generic.cl:28-55 (transformer_methods_cl.py:38-44). */
 int chb_get_phase(double* phs, const double* kx, double x0, int dir, uint32_t Nx, void* stream);
@@ -220,12 +226,16 @@ int chb_dht2(const double* A, uint32_t lda, const double* B, uint32_t ldb, doubl
  * Replaces Reikna FFT `_fft`, methods/transformer_methods_cl.py:482-509, plus the
  * cast / phase / slice-copy passes around it (:295-311, :338-358). */
 int chb_fft_max_pow2(void);
-/* The same transform applied to nbatch <= CHB_MAX_FIELDS arrays in one launch. */
+/* The same transform applied to nbatch <= CHB_MAX_FIELDS arrays in one launch;
+ * out_filter (rows x Nx real, may be NULL) multiplies the output: the spectral
+ * smoothing of fields_smooth, transformer_methods_cl.py:79-85, folded into the
+ * forward transform that precedes it in pic_loop.py:99-103. */
 int chb_fft_x_batched(const double* const* in_host, double* const* out_host, int nbatch,
                       uint32_t rows, uint32_t Nx, size_t in_stride, size_t out_stride,
                       int inverse, int in_real, int out_real, const double* phase,
                       int phase_on_input, const double* twiddles, uint32_t L,
-                      const double* chirp, const double* bfft, void* stream);
+                      const double* chirp, const double* bfft, const double* out_filter,
+                      void* stream);
 int chb_fft_x(const double* in, double* out, uint32_t rows, uint32_t Nx, size_t in_stride,
               size_t out_stride, int inverse, int in_real, int out_real,
               const double* phase, int phase_on_input, const double* twiddles,
