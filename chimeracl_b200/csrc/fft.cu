@@ -123,7 +123,8 @@ struct FftArgs {
   double* out[CHB_MAX_FIELDS];
   size_t in_stride;      // elements between rows (of the input element type)
   size_t out_stride;
-  const double2* tw;     // N (or L for Bluestein) forward roots of unity
+  const double2* tw;     // N (or L for Bluestein) forward roots of unity (N/2 roots for split rows)
+  const double2* tw2;    // split rows: W_N^i, i < N/2
   const double2* phase;  // Nx entries or nullptr
   const double2* chirp;  // Bluestein: exp(-i pi n^2 / N), n < N
   const double2* bfft;   // Bluestein: FFT_L(b)/L
@@ -176,6 +177,36 @@ fft_pow2_kernel(FftArgs a) {
   }
 }
 
+// Rows longer than one CTA's shared memory (N = 16384: 256 KiB): one radix-2
+// decimation-in-frequency stage is folded into the load and the row is shared by TWO
+// CTAs (blockIdx.z = p): CTA p transforms u_p[n] = (x[n] + (-1)^p x[n+N/2]) * W_N^{p n},
+// n < N/2, and owns the outputs X[2k+p].  Both read the whole row (the second read
+// hits L2), each writes every other element.
+template <int LOGH>
+__global__ void __launch_bounds__((1 << LOGH) / 8)
+fft_split2_kernel(FftArgs a) {
+  extern __shared__ double2 s[];
+  constexpr int H = 1 << LOGH, T = H >> 3;
+  const int tid = threadIdx.x, par = blockIdx.z;
+  const double* rin = a.in[blockIdx.y] + (size_t)blockIdx.x * a.in_stride * (a.in_real ? 1 : 2);
+  double* rout = a.out[blockIdx.y] + (size_t)blockIdx.x * a.out_stride * (a.out_real ? 1 : 2);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int i = tid + q * T;
+    const double2 lo = load_in(a, rin, i), hi = load_in(a, rin, i + H);
+    double2 u = par ? csub(lo, hi) : cadd(lo, hi);
+    if (par) u = cmulf(u, __ldg(a.tw2 + i));       // W_N^i, N = 2H
+    s[pad(i)] = u;
+  }
+  __syncthreads();
+  fft_smem_forward<LOGH>(s, a.tw, tid);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int i = tid + q * T;
+    store_out(a, rout, 2 * i + par, s[pad(i)]);
+  }
+}
+
 template <int LOGL>
 __global__ void __launch_bounds__((1 << LOGL) / 8 < 32 ? 32 : (1 << LOGL) / 8)
 fft_bluestein_kernel(FftArgs a) {
@@ -222,7 +253,7 @@ using namespace chb;
 
 extern "C" {
 
-int chb_fft_max_pow2(void) { return 8192; }
+int chb_fft_max_pow2(void) { return 16384; }
 
 int chb_fft_x_batched(const double* const* in_host, double* const* out_host, int nbatch,
                       uint32_t rows, uint32_t Nx, size_t in_stride, size_t out_stride,
@@ -232,8 +263,9 @@ int chb_fft_x_batched(const double* const* in_host, double* const* out_host, int
                       void* stream) {
   if (rows == 0 || Nx == 0 || nbatch == 0) return CHB_OK;
   if (nbatch < 0 || nbatch > CHB_MAX_FIELDS) return CHB_ERR_ARG;
-  if (L < 8 || (L & (L - 1)) || L > 8192) return CHB_ERR_ARG;
+  if (L < 8 || (L & (L - 1)) || L > 16384) return CHB_ERR_ARG;
   const bool pow2 = (L == Nx);
+  if (L > 8192 && !pow2) return CHB_ERR_ARG;   // Bluestein only up to L = 8192
   if (!pow2 && (L < 2 * Nx - 1 || !chirp || !bfft)) return CHB_ERR_ARG;
   FftArgs a;
   for (int k = 0; k < CHB_MAX_FIELDS; ++k) {
@@ -255,6 +287,17 @@ int chb_fft_x_batched(const double* const* in_host, double* const* out_host, int
   int logL = 0;
   while ((1u << logL) < L) ++logL;
   cudaStream_t st = (cudaStream_t)stream;
+  a.tw2 = nullptr;
+  if (L == 16384) {
+    // twiddles = [8192 roots of the half-length transform | 8192 values W_16384^i]
+    a.tw2 = a.tw + 8192;
+    const size_t smem = (size_t)padded_len(8192) * sizeof(double2);
+    cudaError_t e = cudaFuncSetAttribute(fft_split2_kernel<13>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    fft_split2_kernel<13><<<dim3(rows, nbatch, 2), 1024, smem, st>>>(a);
+    CHB_RETURN_LAST_ERROR();
+  }
   switch (logL) {
     case 3: return launch_fft<3>(a, pow2, rows, nbatch, st);
     case 4: return launch_fft<4>(a, pow2, rows, nbatch, st);

@@ -35,6 +35,10 @@ def fft_plan_tables(Nx):
     L = Nx if pow2 else max(_next_pow2(2 * Nx - 1), 8)
     j = np.arange(L)
     tw = np.exp(-2j * np.pi * j / L)
+    if pow2 and L == 16384:
+        # split rows: roots of the half-length transform, then W_L^i for i < L/2
+        h = np.arange(L // 2)
+        tw = np.concatenate((np.exp(-2j * np.pi * h / (L // 2)), np.exp(-2j * np.pi * h / L)))
     if pow2:
         return L, tw, None, None
     n = np.arange(Nx, dtype=np.int64)

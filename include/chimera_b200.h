@@ -222,7 +222,9 @@ int chb_dht2(const double* A, uint32_t lda, const double* B, uint32_t ldb, doubl
  * twiddles: L complex roots exp(-2 pi i j/L).  L == Nx for power-of-two lengths;
  * otherwise Bluestein with L = pow2 >= 2Nx-1, chirp[n] = exp(-i pi n^2/Nx) (Nx
  * entries) and bfft = FFT_L(b)/L (L entries) supplied by the caller (host-side plan,
- * see chimeracl_b200/methods/transformer_methods_cl.py).  8 <= L <= 8192.
+ * see chimeracl_b200/methods/transformer_methods_cl.py).  8 <= L <= 8192, plus
+ * L == Nx == 16384, for which twiddles holds 8192 roots exp(-2 pi i j/8192) followed
+ * by 8192 values exp(-2 pi i j/16384) (one radix-2 stage is split over two CTAs).
  * Replaces Reikna FFT `_fft`, methods/transformer_methods_cl.py:482-509, plus the
  * cast / phase / slice-copy passes around it (:295-311, :338-358). */
 int chb_fft_max_pow2(void);

@@ -16,10 +16,24 @@ import numpy as np
 
 
 class NumpyKernels:
+    """M in {0, 1}: restatement of the reference kernels.  M >= 2 has NO reference
+    particle kernels (grid_deposit_m2.cl does not exist); for it the
+    visible m=1 pattern is generalised -- weights ((y+iz)/r)^m on deposit,
+    2*Re(F_m e^{-i m theta}) on gather -- and parity is UNPINNED."""
     kind = "port"
 
     def __init__(self, M):
         self.M = M
+
+    @staticmethod
+    def _powers(e0, e1, M):
+        """[(Re, Im) of (e0 + i e1)^m for m = 1..M], by the recurrence the CUDA
+        kernels use."""
+        out = [(e0, e1)]
+        for _ in range(1, M):
+            r, i = out[-1]
+            out.append((r * e0 - i * e1, r * e1 + i * e0))
+        return out
 
     # ------------------------------------------------------------------ particles
     def push_xyz(self, x, y, z, px, py, pz, g_inv, dt):
@@ -153,12 +167,13 @@ class NumpyKernels:
             with np.errstate(divide="ignore", invalid="ignore"):
                 rp_inv = 1.0 / rp
                 e0, e1 = yp * rp_inv, zp * rp_inv
+        pw = self._powers(e0, e1, self.M) if self.M >= 1 else []
         for i in range(2):
             for j in range(2):
                 node = ix + j + (ir + i) * Nx
                 self._scatter(flds[0], node, C[i][j])
-                if self.M >= 1:
-                    self._scatter(flds[1], node, (C[i][j] * e0, C[i][j] * e1))
+                for m, (er, ei) in enumerate(pw):
+                    self._scatter(flds[1 + m], node, (C[i][j] * er, C[i][j] * ei))
 
     def depose_vector(self, sort_indx, x, y, z, px, py, pz, g_inv, w,
                       cell_offset, charge, g, flds):
@@ -178,14 +193,15 @@ class NumpyKernels:
             rp_inv = np.zeros_like(rp)
             np.divide(1.0, rp, out=rp_inv, where=rp > 0)
             e0, e1 = yp * rp_inv, zp * rp_inv
+        pw = self._powers(e0, e1, self.M) if self.M >= 1 else []
         for k in range(3):
             for i in range(2):
                 for j in range(2):
                     node = ix + j + (ir + i) * Nx
                     jp_proj = C[i][j] * jp[k]
                     self._scatter(flds[k], node, jp_proj)
-                    if self.M >= 1:
-                        self._scatter(flds[3 + k], node, (jp_proj * e0, jp_proj * e1))
+                    for m, (er, ei) in enumerate(pw):
+                        self._scatter(flds[3 * (m + 1) + k], node, (jp_proj * er, jp_proj * ei))
 
     def treat_axis(self, arr, Nx):
         """grid_generic.cl:37-59: row1 -= row0."""
@@ -225,6 +241,7 @@ class NumpyKernels:
             e1 = -zp * rp_inv
         e_p = [np.zeros_like(xp) for _ in range(3)]
         b_p = [np.zeros_like(xp) for _ in range(3)]
+        pw = self._powers(e0, e1, self.M) if self.M >= 1 else []   # e^{-i m theta}
         for k in range(3):
             for i in range(2):
                 for j in range(2):
@@ -232,13 +249,13 @@ class NumpyKernels:
                     c = C[i][j]
                     e_p[k] = e_p[k] + c * flds[k].reshape(-1)[node]
                     b_p[k] = b_p[k] + c * flds[3 + k].reshape(-1)[node]
-                    if self.M >= 1:
-                        em = flds[6 + k].reshape(-1)[node]
-                        bm = flds[9 + k].reshape(-1)[node]
-                        e_p[k] = e_p[k] + c * (2 * em.real) * e0
-                        e_p[k] = e_p[k] - c * (2 * em.imag) * e1
-                        b_p[k] = b_p[k] + c * (2 * bm.real) * e0
-                        b_p[k] = b_p[k] - c * (2 * bm.imag) * e1
+                    for m, (er, ei) in enumerate(pw):
+                        em = flds[6 * (m + 1) + k].reshape(-1)[node]
+                        bm = flds[6 * (m + 1) + 3 + k].reshape(-1)[node]
+                        e_p[k] = e_p[k] + c * (2 * em.real) * er
+                        e_p[k] = e_p[k] - c * (2 * em.imag) * ei
+                        b_p[k] = b_p[k] + c * (2 * bm.real) * er
+                        b_p[k] = b_p[k] - c * (2 * bm.imag) * ei
         um = [u_p[k] + dt_2 * e_p[k] for k in range(3)]
         g_p_inv = 1.0 / np.sqrt(1.0 + um[0] * um[0] + um[1] * um[1] + um[2] * um[2])
         t = [dt_2 * b_p[k] * g_p_inv for k in range(3)]

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     # pure host-side helper entry points (no device needed)
     assert lib.chb_cell_offsets_workspace_bytes(10 ** 6) >= 4 * (10 ** 6 // 4096)
     assert lib.chb_sort_workspace_bytes(1000, 100) >= 4 * 1000
-    assert lib.chb_fft_max_pow2() == 8192
+    assert lib.chb_fft_max_pow2() == 16384
 
 
 def test_no_cpu_fallback_without_cuda():
@@ -74,6 +74,9 @@ def test_fft_plan_tables(n):
     L, tw, chirp, bfft = fft_plan_tables(n)
     assert L >= 8 and L & (L - 1) == 0
     assert np.allclose(tw, np.exp(-2j * np.pi * np.arange(L) / L))
+    L2, tw2, _, _ = fft_plan_tables(16384)
+    assert L2 == 16384 and tw2.size == 16384
+    assert np.allclose(tw2[8192:], np.exp(-2j * np.pi * np.arange(8192) / 16384))
     if chirp is None:
         assert L == n
         return

@@ -168,3 +168,61 @@ def test_laser_group_velocity_property():
     veloc = 1 - (xc[1:] - xc[:-1]) / S.Args["dt"]
     theory = (2.0 * np.pi * laser["R"]) ** -2
     assert abs(veloc.mean() - theory) / theory < 0.1, (veloc.mean(), theory)
+
+
+@pytest.mark.skipif(not ref_available(1), reason="oracle/_ref not built")
+def test_particle_creation_kernels_match_reference():
+    """fill_grid and profile_by_interpolant (init / injection path,
+    kernels/particles_generic.cl:6-84) against the reference kernels."""
+    Kn, Kr = NumpyKernels(1), RefKernels(1)
+    rng = np.random.default_rng(3)
+    xg = -2.0 + 0.25 * np.arange(9)
+    rg = 0.1 * np.arange(7)
+    th = rng.uniform(0, 2 * np.pi, (xg.size - 1) * (rg.size - 1))
+    a = Kn.fill_grid(th, xg, rg, (2, 3, 4))
+    b = Kr.fill_grid(th, xg, rg, (2, 3, 4))
+    for u, v in zip(a, b):
+        assert np.array_equal(u, v)
+    x = a[0].copy()
+    x_loc = np.array([-3.0, -1.0, 0.5, 3.0])
+    f_loc = np.array([0.0, 0.0, 1.0, 2.0])
+    dxm1 = 1.0 / (x_loc[1:] - x_loc[:-1])
+    w1, w2 = a[3].copy(), a[3].copy()
+    Kn.profile_by_interpolant(x, w1, x_loc, f_loc, dxm1)
+    Kr.profile_by_interpolant(x, w2, x_loc, f_loc, dxm1)
+    assert np.array_equal(w1, w2)
+
+
+def test_mode2_generalisation_reduces_to_mode1():
+    """M=2 particle terms have no reference source (parity unpinned): the
+    generalisation must reduce to the M=1 restatement when nothing lives in m=2."""
+    cfg = {"Xmin": -1.0, "Xmax": 1.0, "Nx": 20, "Rmin": 0.0, "Rmax": 1.0, "Nr": 12}
+    rng = np.random.default_rng(8)
+    n = 4000
+    arrays = dict(x=rng.uniform(-1, 1, n), y=rng.normal(0, 0.4, n), z=rng.normal(0, 0.4, n),
+                  px=rng.normal(0, 1, n), py=rng.normal(0, 1, n), pz=rng.normal(0, 1, n),
+                  w=rng.uniform(0.5, 1, n))
+    arrays["g_inv"] = 1 / np.sqrt(1 + arrays["px"] ** 2 + arrays["py"] ** 2 + arrays["pz"] ** 2)
+    res = {}
+    for M in (1, 2):
+        K = NumpyKernels(M)
+        S = O.OracleSolver(dict(cfg, M=M), K)
+        P = O.OracleParticles({"charge": -1, "dt": 0.05}, K)
+        P.set_particles(**arrays)
+        P.sort_parts(S)
+        S.depose_currents([P])
+        S.depose_charge([P])
+        r2 = np.random.default_rng(9)
+        for k in sorted(S.D):
+            if k[0] in "EB" and "_fb_" not in k and not k.endswith("_m2"):
+                a = r2.normal(size=S.D[k].shape)
+                S.D[k][...] = a if S.D[k].dtype == np.float64 else a + 1j * r2.normal(size=a.shape)
+        S.gather_and_push([P])
+        res[M] = (S, P)
+    (S1, P1), (S2, P2) = res[1], res[2]
+    for k in S1.D:
+        if k.startswith(("rho_m", "J")) and "_fb_" not in k:
+            assert np.array_equal(S1.D[k], S2.D[k]), k
+    assert np.abs(S2.D["rho_m2"]).max() > 0
+    for k in ("px", "py", "pz", "g_inv"):
+        assert np.array_equal(P1.D[k], P2.D[k]), k
