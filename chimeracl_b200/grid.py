@@ -50,7 +50,17 @@ class Grid(GridMethodsCL):
             self.depose_scalar(parts, 'w', 'rho', charge=parts.Args['charge'])
         self.postproc_depose_scalar('rho')
 
-    def depose_currents(self, species=[]):
+    def finish_currents(self):
+        """Complete a depose_currents(..., defer=True): wait for the all-reduce of the
+        raw deposits (multi-GPU) and apply the axis / volume post-processing."""
+        pending = self.__dict__.pop('_pending_J', None)
+        if pending is None:
+            return
+        if pending is not True:
+            pending.wait()
+        self.postproc_depose_vector('J', reduce=False)
+
+    def depose_currents(self, species=[], defer=False):
         comps = self.Args['vec_comps']
         self._flat['J'].zero_()
         for parts in species:
@@ -58,6 +68,12 @@ class Grid(GridMethodsCL):
                 continue
             self.depose_vector(parts, ['p' + comp for comp in comps], ['g_inv', 'w'], 'J',
                                charge=parts.Args['charge'])
+        if defer:
+            # the sum over ranks runs while the caller goes on (second push + sort);
+            # finish_currents() must be called before J is used
+            work = self.start_reduce_currents()
+            self._pending_J = work if work is not None else True
+            return
         self.postproc_depose_vector('J')
 
     def gather_and_push(self, species=[]):

@@ -70,12 +70,13 @@ class GridMethodsCL(GenericMethodsCL):
         else:
             allreduce_sum([a.t for a in arrays], pg)
 
-    def _postproc(self, names):
+    def _postproc(self, names, reduce=True):
         arrays = []
         for name in names:
             arrays += self._mode_fields(name)
-        self._allreduce('rho' if names == ['rho'] else ('J' if names[0][0] == 'J' else None),
-                        arrays)
+        if reduce:
+            self._allreduce('rho' if names == ['rho'] else ('J' if names[0][0] == 'J' else None),
+                            arrays)
         ptrs = _lib.ptr_array([a.ptr for a in arrays])
         flags = _lib.int_array([1 if a.dtype == np.complex128 else 0 for a in arrays])
         self._call('chb_postproc_depose', ptrs, flags, len(arrays), int(self.Args['Nx']),
@@ -84,8 +85,17 @@ class GridMethodsCL(GenericMethodsCL):
     def postproc_depose_scalar(self, fld):
         self._postproc([fld])
 
-    def postproc_depose_vector(self, vec_fld):
-        self._postproc([vec_fld + comp for comp in self.Args['vec_comps']])
+    def postproc_depose_vector(self, vec_fld, reduce=True):
+        self._postproc([vec_fld + comp for comp in self.Args['vec_comps']], reduce=reduce)
+
+    def start_reduce_currents(self):
+        """Multi-GPU: launch the sum of the raw J deposits over ranks asynchronously."""
+        pg = getattr(self.comm, 'process_group', None)
+        flat = getattr(self, '_flat', {}).get('J')
+        if pg is None or flat is None:
+            return None
+        from ..parallel import allreduce_sum_async
+        return allreduce_sum_async(flat, pg)
 
     # ------------------------------------------------------------------ gather
     def preproc_project_vec(self, vec_fld):

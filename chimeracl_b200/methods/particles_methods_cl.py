@@ -169,27 +169,26 @@ class ParticleMethodsCL(GenericMethodsCL):
             return
         which_dt = 'dt_2' if mode == 'half' else 'dt'
         D = self.DataDev
-        if getattr(self, 'fuse_push_sort', False):
-            # executed together with the cell indexing in the next sort_parts()
-            # (one pass over the particles, chb_push_index); flushed by anything
-            # else that looks at the coordinates
-            self._flush_pending_push()
-            self._pending_push = which_dt
-        else:
-            self._call('chb_push_xyz', D['x'].ptr, D['y'].ptr, D['z'].ptr, D['px'].ptr,
-                       D['py'].ptr, D['pz'].ptr, D['g_inv'].ptr, D[which_dt].ptr,
-                       int(self.Args['Np']))
-        self.flag_sorted = False
-
-    def _flush_pending_push(self):
-        which_dt = self._pending_push
-        if which_dt is None:
-            return
-        self._pending_push = None
-        D = self.DataDev
         self._call('chb_push_xyz', D['x'].ptr, D['y'].ptr, D['z'].ptr, D['px'].ptr,
                    D['py'].ptr, D['pz'].ptr, D['g_inv'].ptr, D[which_dt].ptr,
                    int(self.Args['Np']))
+        self.flag_sorted = False
+
+    def push_and_sort(self, grid, mode='half'):
+        """push_coords(mode) immediately followed by sort_parts(grid) -- the pair
+        pic_loop.py:70-76 issues twice per step -- as ONE pass over the particles
+        (chb_push_index computes the cell index and histogram while the pushed
+        coordinates are still in registers).  Same results as the two calls."""
+        if self.Args['Np'] == 0 or 'Immobile' in self.Args.keys():
+            self.push_coords(mode)
+            self.sort_parts(grid)
+            return
+        self._pending_push = 'dt_2' if mode == 'half' else 'dt'
+        self.flag_sorted = False
+        try:
+            self.sort_parts(grid)
+        finally:
+            self._pending_push = None
 
     def index_sort(self, grid):
         lib, st = self._lib, self._stream

@@ -35,6 +35,18 @@ def shard_range(n, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def allreduce_sum_async(flat, group=None):
+    """Start an in-place sum over ranks of one flat real tensor on the collective's own
+    stream and return the work handle (None for a single rank); `handle.wait()` makes
+    the caller's stream wait for it.  Lets the J all-reduce overlap the second
+    push + sort of the step."""
+    if group is None and not dist.is_initialized():
+        return None
+    if dist.get_world_size(group) == 1:
+        return None
+    return dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=True)
+
+
 def allreduce_sum(tensors, group=None):
     """In-place sum over ranks of a list of (real or complex) tensors.  The arrays
     are packed into one flat FP64 buffer so that the exchange is a single

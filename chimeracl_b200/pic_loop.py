@@ -23,8 +23,7 @@ class PIC_loop:
         self.diags = diags
         self.timit = timit
         self.it = 0
-        for parts in self.species:
-            parts.fuse_push_sort = bool(fuse_push_sort)
+        self.fuse_push_sort = bool(fuse_push_sort)
         if self.timit is True:
             self.Timer = {key: 0 for key in loop_steps}
             self._events = []
@@ -65,13 +64,18 @@ class PIC_loop:
 
         self.timer_start()
         for solver in self.solvers:
-            solver.depose_currents(species=self.species)
+            if hasattr(solver, 'finish_currents'):
+                solver.depose_currents(species=self.species, defer=True)
+            else:
+                solver.depose_currents(species=self.species)
         self.timer_record('depose')
 
         self._push_and_sort()
 
         for solver in self.solvers:
             self.timer_start()
+            if hasattr(solver, 'finish_currents'):
+                solver.finish_currents()       # J: all-reduce (multi-GPU) + axis / dV
             solver.depose_charge(species=self.species)
             self.timer_record('depose')
 
@@ -123,6 +127,11 @@ class PIC_loop:
 
     def _push_and_sort(self):
         for parts in self.species:
+            if self.fuse_push_sort and hasattr(parts, 'push_and_sort'):
+                self.timer_start()
+                parts.push_and_sort(self.mainsolver, mode='half')   # one fused pass
+                self.timer_record('sort')
+                continue
             self.timer_start()
             parts.push_coords(mode='half')
             self.timer_record('push-x')

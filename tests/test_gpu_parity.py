@@ -63,10 +63,12 @@ def test_push_and_sort_bit_exact(comm, M, fused):
     G = load_golden(M)
     S, P, I = gpu_case_from_golden(G, comm)
     So, Po, Io = oracle_case_from_golden(G, NumpyKernels(M))
-    P.fuse_push_sort = fused
     for p, po in ((P, Po), (I, Io)):
-        p.push_coords("half")
-        p.sort_parts(S)
+        if fused:
+            p.push_and_sort(S, "half")
+        else:
+            p.push_coords("half")
+            p.sort_parts(S)
         po.push_coords("half")
         po.sort_parts(So)
     for k in ("x", "y", "z"):
