@@ -45,7 +45,67 @@ struct DepArgs {
   GridGeom geom;
   int charge;
   uint32_t ncells;
+  // PUSH variant only: coordinates are advanced by dt*g_inv*p before the deposit
+  double* xw;
+  double* yw;
+  double* zw;
+  const double* __restrict__ dt_dev;
+  uint32_t np_total;
+  uint32_t* exc_count;   // PUSH: number of / sorted positions of the particles that are
+  uint32_t* exc_list;    //       no longer in the cell the traversal order assumes
 };
+
+// Deposit of ONE particle straight to global memory (REDs): used for the few
+// particles whose cell is not the one the traversal order assumes.  Same operation
+// order as the reference depose_vector (grid_deposit_m1.cl:268-310).
+template <int M>
+__device__ __noinline__ void deposit_direct(double* const* out, const GridVals& g,
+                                               double xp, double yp, double zp, double jx,
+                                               double jy, double jz, double wp) {
+  constexpr int MM = M > 0 ? M : 1;
+  double rp;
+  int ix, ir;
+  cell_coords(xp, yp, zp, g, rp, ix, ir);
+  const double rinv = !(rp > 0.0) ? 0.0 : __drcp_rn(rp);
+  double er[MM], ei[MM];
+  er[0] = __dmul_rn(yp, rinv);
+  ei[0] = __dmul_rn(zp, rinv);
+#pragma unroll
+  for (int m = 1; m < MM; ++m) {
+    er[m] = er[m - 1] * er[0] - ei[m - 1] * ei[0];
+    ei[m] = er[m - 1] * ei[0] + ei[m - 1] * er[0];
+  }
+  double sX1 = __dsub_rn(__dmul_rn(__dsub_rn(xp, g.xmin), g.dx_inv), (double)ix);
+  double sX0 = __dsub_rn(1.0, sX1);
+  const double sR1 = __dsub_rn(__dmul_rn(__dsub_rn(rp, g.rmin), g.dr_inv), (double)ir);
+  const double sR0 = __dsub_rn(1.0, sR1);
+  sX0 = __dmul_rn(sX0, wp);
+  sX1 = __dmul_rn(sX1, wp);
+  const double C[4] = {__dmul_rn(sR0, sX0), __dmul_rn(sR0, sX1), __dmul_rn(sR1, sX0),
+                       __dmul_rn(sR1, sX1)};
+  const double jk[3] = {jx, jy, jz};
+#pragma unroll
+  for (int n = 0; n < 4; ++n) {
+    const size_t node = (size_t)(ix + (n & 1)) + (size_t)(ir + (n >> 1)) * (size_t)g.Nx;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double pj = __dmul_rn(C[n], jk[k]);
+      red_add_f64(out[k] + node, pj);
+      if (M > 0) {
+#pragma unroll
+        for (int m = 0; m < MM; ++m) {
+          double* o = out[(m + 1) * 3 + k] + 2 * node;
+          red_add_f64(o, pj * er[m]);
+          red_add_f64(o + 1, pj * ei[m]);
+        }
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ bool cell_valid(int ix, int ir, const GridVals& g) {
+  return ix > 0 && ix < g.Nx - 2 && ir < g.Nr - 2 && ir >= 0;
+}
 
 // Threads per CTA: one thread per (cell, component) -- the three current components
 // of a cell are accumulated by three threads (each in a different warp, so the
@@ -62,9 +122,16 @@ struct DepSmem {
   static constexpr int kBytes = 2 * kSlots * kDepPad * (int)sizeof(double);  // double buffered
 };
 
-template <int M, bool VEC>
+// PUSH (J only): the traversal order (sort_indx / cell_offset) is the one of the
+// PREVIOUS sort; every particle is first advanced by the half step (written back),
+// then deposited -- through the cell-ordered fast path if it is still in the cell the
+// order assumes, else (a few per cent) through deposit_direct.  This folds
+// push_coords('half') + sort_parts + depose_currents of pic_loop.py:70-81 into one
+// pass and removes one full sort per step.
+template <int M, bool VEC, bool PUSH = false>
 __global__ void __launch_bounds__(DepShape<VEC>::kThreads, VEC ? 3 : 6)
 depose_kernel(DepArgs<M, VEC> a) {
+  static_assert(!PUSH || VEC, "the fused push exists for the current deposit only");
   constexpr int NC = VEC ? 3 : 1;
   constexpr int NT = DepShape<VEC>::kThreads;
   constexpr int MM = M > 0 ? M : 1;
@@ -81,6 +148,7 @@ depose_kernel(DepArgs<M, VEC> a) {
   const GridVals g = load_geom(a.geom);
   const int Nx_cell = g.Nx - 1;
   const double q = (double)a.charge;
+  const double dt = PUSH ? __ldg(a.dt_dev) : 0.0;
 
   const uint32_t c0 = blockIdx.x * kDepCells;
   const uint32_t c1 = min(c0 + (uint32_t)kDepCells, a.ncells);
@@ -108,6 +176,7 @@ depose_kernel(DepArgs<M, VEC> a) {
 
   // sorted indices of the particles this thread stages in the NEXT issued batch
   uint32_t sidx[KP];
+  uint32_t sprev[PUSH ? KP : 1];   // ... and of the batch in flight (PUSH: write-back)
   auto load_sidx = [&](uint32_t b0) {
 #pragma unroll
     for (int k = 0; k < KP; ++k) {
@@ -120,6 +189,7 @@ depose_kernel(DepArgs<M, VEC> a) {
 #pragma unroll
     for (int k = 0; k < KP; ++k) {
       const uint32_t s = sidx[k];
+      if (PUSH) sprev[k] = s;
       if (s == 0xffffffffu) continue;
       const int p = pidx((int)(threadIdx.x + k * NT));
       cp_async8(&slot(buf, 0, p), a.x + s);
@@ -144,10 +214,19 @@ depose_kernel(DepArgs<M, VEC> a) {
       const uint32_t j = b0 + threadIdx.x + k * NT;
       if (!(j < P1 && threadIdx.x + k * NT < kDepBatch)) continue;
       const int p = pidx((int)(threadIdx.x + k * NT));
-      const double xp = slot(buf, 0, p), yp = slot(buf, 1, p), zp = slot(buf, 2, p);
+      double xp = slot(buf, 0, p), yp = slot(buf, 1, p), zp = slot(buf, 2, p);
       double wp;
       if (VEC) wp = __dmul_rn(__dmul_rn(slot(buf, 6, p), slot(buf, 7, p)), q);
       else wp = __dmul_rn(slot(buf, 3, p), q);
+      if (PUSH) {
+        // half push, same arithmetic as push_xyz (particles_generic.cl:142-151)
+        const uint32_t s = sprev[k];
+        const double dt_g = __dmul_rn(dt, slot(buf, 7, p));
+        xp = __dadd_rn(xp, __dmul_rn(slot(buf, 3, p), dt_g));
+        yp = __dadd_rn(yp, __dmul_rn(slot(buf, 4, p), dt_g));
+        zp = __dadd_rn(zp, __dmul_rn(slot(buf, 5, p), dt_g));
+        a.xw[s] = xp; a.yw[s] = yp; a.zw[s] = zp;
+      }
       const double rp = __dsqrt_rn(__dadd_rn(__dmul_rn(yp, yp), __dmul_rn(zp, zp)));
       slot(buf, 0, p) = __dmul_rn(__dsub_rn(xp, g.xmin), g.dx_inv);
       slot(buf, 1, p) = __dmul_rn(__dsub_rn(rp, g.rmin), g.dr_inv);
@@ -185,6 +264,14 @@ depose_kernel(DepArgs<M, VEC> a) {
       double sX0 = __dsub_rn(1.0, sX1);
       const double sR1 = __dsub_rn(slot(buf, 1, p), dir_);
       const double sR0 = __dsub_rn(1.0, sR1);
+      if (PUSH) {
+        // floor(ax) == ix  <=>  0 <= ax - ix < 1 (the subtraction is exact): a particle
+        // that left this cell during the push goes to the exception list instead
+        if (!(sX1 >= 0.0 && sX1 < 1.0 && sR1 >= 0.0 && sR1 < 1.0)) {
+          if (comp == 0) a.exc_list[atomicAdd(a.exc_count, 1u)] = j;
+          continue;
+        }
+      }
       sX0 = __dmul_rn(sX0, wp);
       sX1 = __dmul_rn(sX1, wp);
       double pj[4] = {__dmul_rn(sR0, sX0), __dmul_rn(sR0, sX1),
@@ -236,14 +323,53 @@ depose_kernel(DepArgs<M, VEC> a) {
   }
 }
 
-template <int M, bool VEC>
+// PUSH: particles beyond the last real cell of the previous sort (its trash bin) are
+// pushed too and, should they have re-entered the box, deposited directly.
+template <int M>
+__global__ void __launch_bounds__(256)
+depose_push_tail_kernel(DepArgs<M, true> a) {
+  const GridVals g = load_geom(a.geom);
+  const double dt = __ldg(a.dt_dev);
+  const double q = (double)a.charge;
+  const uint32_t first = __ldg(a.cell_offset + a.ncells);
+  for (uint32_t j = first + blockIdx.x * blockDim.x + threadIdx.x; j < a.np_total;
+       j += gridDim.x * blockDim.x) {
+    const uint32_t s = __ldg(a.sort_indx + j);
+    const double ux = a.px[s], uy = a.py[s], uz = a.pz[s], gi = a.g_inv[s];
+    const double dt_g = __dmul_rn(dt, gi);
+    const double xp = __dadd_rn(a.xw[s], __dmul_rn(ux, dt_g));
+    const double yp = __dadd_rn(a.yw[s], __dmul_rn(uy, dt_g));
+    const double zp = __dadd_rn(a.zw[s], __dmul_rn(uz, dt_g));
+    a.xw[s] = xp; a.yw[s] = yp; a.zw[s] = zp;
+    double r_;
+    int ix, ir;
+    cell_coords(xp, yp, zp, g, r_, ix, ir);
+    if (cell_valid(ix, ir, g))
+      deposit_direct<M>(a.out, g, xp, yp, zp, ux, uy, uz,
+                        __dmul_rn(__dmul_rn(a.w[s], gi), q));
+  }
+  // particles (already pushed) that changed cell: deposit at their new position
+  const uint32_t nexc = *a.exc_count;
+  for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < nexc; e += gridDim.x * blockDim.x) {
+    const uint32_t s = __ldg(a.sort_indx + a.exc_list[e]);
+    const double xp = a.xw[s], yp = a.yw[s], zp = a.zw[s];
+    double r_;
+    int ix, ir;
+    cell_coords(xp, yp, zp, g, r_, ix, ir);
+    if (cell_valid(ix, ir, g))
+      deposit_direct<M>(a.out, g, xp, yp, zp, a.px[s], a.py[s], a.pz[s],
+                        __dmul_rn(__dmul_rn(a.w[s], a.g_inv[s]), q));
+  }
+}
+
+template <int M, bool VEC, bool PUSH = false>
 static int launch_depose(DepArgs<M, VEC>& a, cudaStream_t st) {
   uint32_t grid = (a.ncells + kDepCells - 1) / kDepCells;
   constexpr int smem = DepSmem<M, VEC>::kBytes;
-  cudaError_t e = cudaFuncSetAttribute(depose_kernel<M, VEC>,
+  cudaError_t e = cudaFuncSetAttribute(depose_kernel<M, VEC, PUSH>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return (int)e;
-  depose_kernel<M, VEC><<<grid, DepShape<VEC>::kThreads, smem, st>>>(a);
+  depose_kernel<M, VEC, PUSH><<<grid, DepShape<VEC>::kThreads, smem, st>>>(a);
   CHB_RETURN_LAST_ERROR();
 }
 
@@ -314,7 +440,8 @@ int chb_depose_scalar(int M, const uint32_t* sort_indx, const double* x, const d
 #define CHB_GO(MM)                                                              \
   {                                                                             \
     DepArgs<MM, false> a{sort_indx, x, y, z, nullptr, nullptr, nullptr, nullptr, w, \
-                         cell_offset, {}, g, charge, (Nx - 1) * (Nr - 1)};      \
+                         cell_offset, {}, g, charge, (Nx - 1) * (Nr - 1),       \
+                         nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr}; \
     for (int k = 0; k < MM + 1; ++k) a.out[k] = rho_host[k];                    \
     return launch_depose<MM, false>(a, st);                                     \
   }
@@ -338,9 +465,48 @@ int chb_depose_vector(int M, const uint32_t* sort_indx, const double* x, const d
 #define CHB_GO(MM)                                                              \
   {                                                                             \
     DepArgs<MM, true> a{sort_indx, x, y, z, px, py, pz, g_inv, w, cell_offset,  \
-                        {}, g, charge, (Nx - 1) * (Nr - 1)};                    \
+                        {}, g, charge, (Nx - 1) * (Nr - 1),                     \
+                        nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr}; \
     for (int k = 0; k < 3 * (MM + 1); ++k) a.out[k] = j_host[k];                \
     return launch_depose<MM, true>(a, st);                                      \
+  }
+  switch (M) {
+    case 0: CHB_GO(0)
+    case 1: CHB_GO(1)
+    default: CHB_GO(2)
+  }
+#undef CHB_GO
+}
+
+int chb_push_depose_vector(int M, const uint32_t* sort_indx, double* x, double* y, double* z,
+                           const double* px, const double* py, const double* pz,
+                           const double* g_inv, const double* w,
+                           const uint32_t* cell_offset, const double* dt_dev, uint32_t np,
+                           int charge, uint32_t Nx, uint32_t Nr, const double* xmin,
+                           const double* dx_inv, const double* rmin, const double* dr_inv,
+                           double* const* j_host, void* workspace, size_t workspace_bytes,
+                           void* stream) {
+  if (M < 0 || M >= CHB_MAX_MODES || Nx < 3 || Nr < 3) return CHB_ERR_ARG;
+  if (np == 0) return CHB_OK;
+  if (workspace_bytes < ((size_t)np + 1) * sizeof(uint32_t)) return CHB_ERR_WORKSPACE;
+  GridGeom g{xmin, dx_inv, rmin, dr_inv, Nx, Nr};
+  cudaStream_t st = (cudaStream_t)stream;
+  uint32_t* exc_count = (uint32_t*)workspace;
+  uint32_t* exc_list = exc_count + 1;
+  {
+    cudaError_t e = cudaMemsetAsync(exc_count, 0, sizeof(uint32_t), st);
+    if (e != cudaSuccess) return (int)e;
+  }
+#define CHB_GO(MM)                                                              \
+  {                                                                             \
+    DepArgs<MM, true> a{sort_indx, x, y, z, px, py, pz, g_inv, w, cell_offset,  \
+                        {}, g, charge, (Nx - 1) * (Nr - 1), x, y, z, dt_dev, np,  \
+                        exc_count, exc_list};                                   \
+    for (int k = 0; k < 3 * (MM + 1); ++k) a.out[k] = j_host[k];                \
+    int rc = launch_depose<MM, true, true>(a, st);                              \
+    if (rc) return rc;                                                          \
+    depose_push_tail_kernel<MM><<<kSMs, 256, 0, st>>>(a);                       \
+    CHB_RETURN_LAST_ERROR();                                                    \
   }
   switch (M) {
     case 0: CHB_GO(0)

@@ -60,14 +60,18 @@ class Grid(GridMethodsCL):
             pending.wait()
         self.postproc_depose_vector('J', reduce=False)
 
-    def depose_currents(self, species=[], defer=False):
+    def depose_currents(self, species=[], defer=False, push_mode=None):
         comps = self.Args['vec_comps']
         self._flat['J'].zero_()
         for parts in species:
             if 'Immobile' in parts.Args.keys():
                 continue
+            push_dt = None
+            if push_mode is not None:
+                # fused push_coords(push_mode) + sort_parts + deposit for this species
+                push_dt = 'dt_2' if push_mode == 'half' else 'dt'
             self.depose_vector(parts, ['p' + comp for comp in comps], ['g_inv', 'w'], 'J',
-                               charge=parts.Args['charge'])
+                               charge=parts.Args['charge'], push_dt=push_dt)
         if defer:
             # the sum over ranks runs while the caller goes on (second push + sort);
             # finish_currents() must be called before J is used

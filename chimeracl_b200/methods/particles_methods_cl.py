@@ -42,7 +42,23 @@ class ParticleMethodsCL(GenericMethodsCL):
         return ['x', 'y', 'z', 'px', 'py', 'pz', 'w', 'g_inv']
 
     # ------------------------------------------------------------------ creation
+    def traversal_order_valid(self, grid):
+        """True if sort_indx / cell_offset still describe a permutation of the current
+        storage computed on `grid` (no particles added since the last sort): they can
+        then serve as the traversal order of the fused push + deposit."""
+        return (self.Args['Np'] > 0 and getattr(self, '_order_np', -1) == self.Args['Np']
+                and getattr(self, '_order_grid', None) is grid
+                and 'sort_indx' in self.DataDev
+                and self.DataDev['sort_indx'].size == self.Args['Np'])
+
+    def exception_workspace(self):
+        """(pointer, bytes) of the (Np+1) x u32 scratch chb_push_depose_vector needs."""
+        n = int(self.Args['Np']) + 1
+        ws = self._buf('exc_ws', n, np.uint32)
+        return ws.ptr, n * 4
+
     def add_new_particles(self, source=None):
+        self._order_np = -1
         DataSrc = self.DataDev if source is None else source.DataDev
         for arg in self._attr_names():
             self.DataDev[arg] = DevArray(torch.cat((self.DataDev[arg].t,
@@ -197,6 +213,7 @@ class ParticleMethodsCL(GenericMethodsCL):
         nbins = int(grid.Args['Nxm1Nrm1']) + 1
         Nx, Nr = int(grid.Args['Nx']), int(grid.Args['Nr'])
 
+        self._order_np, self._order_grid = Np, grid
         D['indx_in_cell'] = self._buf('indx_in_cell', Np, np.uint32)
         D['sum_in_cell'] = self._buf('sum_in_cell', nbins, np.uint32)
         D['cell_offset'] = self._buf('cell_offset', nbins + 1, np.uint32)
@@ -260,6 +277,10 @@ class ParticleMethodsCL(GenericMethodsCL):
             self.DataDev[comp] = arr
         self.DataDev['sort_indx'] = sort_new
         self.reset_num_parts()
+        # storage now IS the sorted order; cell_offset stays valid for the real cells,
+        # but the trash tail is gone: cell_offset[-1] must end at the new Np
+        self.DataDev['cell_offset'][-1:] = self.DataDev['cell_offset'][-2:-1]
+        self._order_np = Np_stay
 
     def reset_num_parts(self, Np=None):
         if Np is None:

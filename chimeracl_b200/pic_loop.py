@@ -60,11 +60,19 @@ class PIC_loop:
                 frame.inject_plasma(species=self.species, grid=self.mainsolver)
         self.timer_record('frame')
 
-        self._push_and_sort()
+        # first half push + sort + current deposit.  When every mobile species still
+        # has the previous step's sort as a valid traversal order, the three are ONE
+        # pass (chb_push_depose_vector) and the first sort of the step is not needed.
+        fuse_first = self.fuse_push_sort and len(self.solvers) == 1 and \
+            hasattr(self.mainsolver, 'finish_currents') and self._can_fuse_first_half()
+        if not fuse_first:
+            self._push_and_sort()
 
         self.timer_start()
         for solver in self.solvers:
-            if hasattr(solver, 'finish_currents'):
+            if fuse_first:
+                solver.depose_currents(species=self.species, defer=True, push_mode='half')
+            elif hasattr(solver, 'finish_currents'):
                 solver.depose_currents(species=self.species, defer=True)
             else:
                 solver.depose_currents(species=self.species)
@@ -124,6 +132,15 @@ class PIC_loop:
 
         self.it += 1
         return self.it
+
+    def _can_fuse_first_half(self):
+        for parts in self.species:
+            if 'Immobile' in parts.Args.keys() or parts.Args['Np'] == 0:
+                continue
+            if not (hasattr(parts, 'traversal_order_valid')
+                    and parts.traversal_order_valid(self.mainsolver)):
+                return False
+        return True
 
     def _push_and_sort(self):
         for parts in self.species:

@@ -111,6 +111,23 @@ int chb_depose_vector(int M, const uint32_t* sort_indx, const double* x, const d
                       const double* xmin, const double* dx_inv, const double* rmin,
                       const double* dr_inv, double* const* j_host, void* stream);
 
+/* Fusion of push_coords(dt) + sort_parts + depose_currents (pic_loop.py:70-81): every
+ * particle is advanced by dt*g_inv*p (x, y, z updated in place, same arithmetic as
+ * chb_push_xyz) and its current deposited at the NEW position.  sort_indx /
+ * cell_offset are those of the PREVIOUS sort and only serve as traversal order:
+ * particles still in the cell that order assumes take the cell-ordered fast path, the
+ * others (and the previous trash bin) are deposited one by one.  Same sums as
+ * chb_push_xyz -> sort -> chb_depose_vector up to summation order; np = all particles;
+ * workspace: (np + 1) * 4 bytes (list of the particles that changed cell). */
+int chb_push_depose_vector(int M, const uint32_t* sort_indx, double* x, double* y, double* z,
+                           const double* px, const double* py, const double* pz,
+                           const double* g_inv, const double* w,
+                           const uint32_t* cell_offset, const double* dt_dev, uint32_t np,
+                           int charge, uint32_t Nx, uint32_t Nr, const double* xmin,
+                           const double* dx_inv, const double* rmin, const double* dr_inv,
+                           double* const* j_host, void* workspace, size_t workspace_bytes,
+                           void* stream);
+
 /* row1 -= row0, then arr[ir,:] *= dV_inv[ir], for nfld arrays in one launch
  * (is_complex_host[k] != 0 for complex arrays).  Replaces treat_axis_{d,c} and
  * divide_by_dv_{d,c}, kernels/grid_generic.cl:4-59 (grid_methods_cl.py:98-151). */

@@ -476,3 +476,44 @@ def test_particle_creation_matches_oracle(comm):
     w = ref[3].copy()
     NumpyKernels(1).profile_by_interpolant(ref[0], w, x_loc, f_loc, 1.0 / np.diff(x_loc))
     assert rel_err(P.DataDev["w_new"].get(), w) < 1e-14
+
+
+@pytest.mark.parametrize("M", [0, 1])
+def test_fused_push_deposit_equals_push_sort_deposit(comm, M):
+    """chb_push_depose_vector (half push + current deposit along the PREVIOUS sort)
+    against push_coords -> sort_parts -> depose_currents, with fast particles so that
+    many change cell, leave the box or come back from the trash bin."""
+    from chimeracl_b200.solver import Solver
+    from chimeracl_b200.particles import Particles
+    cfg = {"Xmin": -1.0, "Xmax": 1.0, "Nx": 48, "Rmin": 0.0, "Rmax": 1.0, "Nr": 24, "M": M}
+    S1, S2 = Solver(dict(cfg), comm), Solver(dict(cfg), comm)
+    rng = np.random.default_rng(77)
+    n = 120000
+    arrays = {"x": rng.uniform(-1.15, 1.15, n), "y": rng.normal(0, 0.45, n),
+              "z": rng.normal(0, 0.45, n), "px": rng.normal(0, 2, n), "py": rng.normal(0, 2, n),
+              "pz": rng.normal(0, 2, n), "w": rng.uniform(0.5, 1.5, n)}
+    arrays["g_inv"] = 1 / np.sqrt(1 + arrays["px"] ** 2 + arrays["py"] ** 2 + arrays["pz"] ** 2)
+    pcfg = {"charge": -1, "dt": 0.08}
+    P1, P2 = Particles(dict(pcfg), comm), Particles(dict(pcfg), comm)
+    for P, S in ((P1, S1), (P2, S2)):
+        set_particles(P, arrays)
+        P.sort_parts(S)                       # the "previous step's" sort
+    assert P2.traversal_order_valid(S2)
+    # reference sequence
+    P1.push_coords("half")
+    P1.sort_parts(S1)
+    S1.depose_currents([P1])
+    # fused
+    S2.depose_currents([P2], push_mode="half")
+    assert P2.flag_sorted is False
+    for k in ("x", "y", "z"):
+        assert np.array_equal(P1.DataDev[k].get(), P2.DataDev[k].get()), k
+    moved = (P1.DataDev["indx_in_cell"].get() != P2.DataDev["indx_in_cell"].get()).mean()
+    assert moved > 0.2                        # the exception path is really exercised
+    for k in S1.DataDev:
+        if k.startswith(("Jx_m", "Jy_m", "Jz_m")):
+            assert rel_err(S2.DataDev[k].get(), S1.DataDev[k].get()) < 1e-12, k
+    # and the next sort is the same
+    P2.sort_parts(S2)
+    check_equal = [np.array_equal(P1.DataDev[k].get(), P2.DataDev[k].get()) for k in INT_KEYS]
+    assert all(check_equal)
