@@ -44,10 +44,27 @@ class Grid(GridMethodsCL):
         self._init_grid_data_on_dev()
         self.send_args_to_dev()
 
-    def depose_charge(self, species=[]):
+    def finish_charge(self):
+        """Complete a depose_charge(..., defer=True) (see finish_currents)."""
+        pending = self.__dict__.pop('_pending_rho', None)
+        if pending is None:
+            return
+        if pending is not True:
+            pending.wait()
+        self._postproc(['rho'], reduce=False)
+
+    def depose_charge(self, species=[], defer=False):
         self._flat['rho'].zero_()
         for parts in species:
             self.depose_scalar(parts, 'w', 'rho', charge=parts.Args['charge'])
+        if defer:
+            pg = getattr(self.comm, 'process_group', None)
+            work = None
+            if pg is not None:
+                from .parallel import allreduce_sum_async
+                work = allreduce_sum_async(self._flat['rho'], pg)
+            self._pending_rho = work if work is not None else True
+            return
         self.postproc_depose_scalar('rho')
 
     def finish_currents(self):

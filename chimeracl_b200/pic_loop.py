@@ -84,13 +84,21 @@ class PIC_loop:
             self.timer_start()
             if hasattr(solver, 'finish_currents'):
                 solver.finish_currents()       # J: all-reduce (multi-GPU) + axis / dV
-            solver.depose_charge(species=self.species)
+            multi = getattr(solver.comm, 'process_group', None) is not None and \
+                hasattr(solver, 'finish_charge')
+            solver.depose_charge(species=self.species, **({'defer': True} if multi else {}))
             self.timer_record('depose')
 
             # forward transform with the spectral smoothing (reference: a separate
-            # fields_smooth(['rho','Jx','Jy','Jz']) pass) folded into its last stage
+            # fields_smooth(['rho','Jx','Jy','Jz']) pass) folded into its last stage.
+            # Multi-GPU: J is transformed while the all-reduce of rho is in flight.
             self.timer_start()
-            solver.fb_transform(scals=['rho', ], vects=['J', ], dir=0, smooth=True)
+            if multi:
+                solver.fb_transform(vects=['J', ], dir=0, smooth=True)
+                solver.finish_charge()
+                solver.fb_transform(scals=['rho', ], dir=0, smooth=True)
+            else:
+                solver.fb_transform(scals=['rho', ], vects=['J', ], dir=0, smooth=True)
             self.timer_record('transform')
 
             self.timer_start()

@@ -30,6 +30,7 @@ def main():
         p.sort_parts(solver)
         p.align_parts()
     loop = PIC_loop(solvers=[solver], species=[eons, ions])
+    loop.step()          # the first step cannot use the fused push+deposit (no previous sort)
     torch.cuda.synchronize()
     torch.cuda.profiler.start()
     for _ in range(a.steps):
