@@ -61,63 +61,6 @@ __device__ __forceinline__ void dft8(double2* v) {
 __device__ __forceinline__ int pad(int i) { return i + (i >> 3); }
 __host__ __device__ constexpr int padded_len(int n) { return n + (n >> 3); }
 
-// One Stockham pass of radix 2^LR at sub-transform length NS over s[0..N).
-template <int LOGN, int LR, int NS>
-__device__ __forceinline__ void stockham_pass(double2* s, const double2* __restrict__ tw, int tid) {
-  constexpr int N = 1 << LOGN, T = N >> 3, R = 1 << LR, NB = 8 >> LR;
-  double2 v[8];
-#pragma unroll
-  for (int q = 0; q < NB; ++q) {
-    const int j = tid + q * T;
-#pragma unroll
-    for (int r = 0; r < R; ++r) v[q * R + r] = s[pad(j + r * (N / R))];
-  }
-  __syncthreads();
-#pragma unroll
-  for (int q = 0; q < NB; ++q) {
-    const int j = tid + q * T;
-    const int k = j & (NS - 1);
-    double2* b = v + q * R;
-    if (NS > 1) {
-      const double2 w1 = __ldg(tw + (size_t)k * (N / (NS * R)));
-      double2 w = w1;
-#pragma unroll
-      for (int r = 1; r < R; ++r) {
-        b[r] = cmulf(b[r], w);
-        if (r + 1 < R) w = cmulf(w, w1);
-      }
-    }
-    if (LR == 3) dft8(b);
-    else if (LR == 2) dft4(b[0], b[1], b[2], b[3]);
-    else dft2(b[0], b[1]);
-    const int j0 = ((j - k) << LR) + k;   // (j / NS) * NS * R + k
-#pragma unroll
-    for (int r = 0; r < R; ++r) s[pad(j0 + r * NS)] = b[r];
-  }
-  __syncthreads();
-}
-
-template <int LOGN, int DONE, int NS>
-struct Passes {
-  static __device__ __forceinline__ void run(double2* s, const double2* __restrict__ tw, int tid) {
-    constexpr int REM = LOGN - DONE;
-    constexpr int LR = REM >= 3 ? 3 : REM;
-    stockham_pass<LOGN, LR, NS>(s, tw, tid);
-    Passes<LOGN, DONE + LR, (NS << LR)>::run(s, tw, tid);
-  }
-};
-template <int LOGN, int NS>
-struct Passes<LOGN, LOGN, NS> {
-  static __device__ __forceinline__ void run(double2*, const double2* __restrict__, int) {}
-};
-
-// In-place forward FFT of the padded buffer s (natural order in, natural order
-// out), executed by exactly N/8 threads; tw[j] = exp(-2 pi i j / N).
-template <int LOGN>
-__device__ __forceinline__ void fft_smem_forward(double2* s, const double2* __restrict__ tw, int tid) {
-  Passes<LOGN, 0, 1>::run(s, tw, tid);
-}
-
 struct FftArgs {
   const double* in[CHB_MAX_FIELDS];   // real or complex rows, one entry per batched array
   double* out[CHB_MAX_FIELDS];
@@ -155,6 +98,80 @@ __device__ __forceinline__ void store_out(const FftArgs& a, double* row, int ix,
   else reinterpret_cast<double2*>(row)[ix] = v;
 }
 
+// One Stockham pass of radix 2^LR at sub-transform length NS over s[0..N).
+// FIRST: the inputs come straight from global memory (with the fused prologue) instead
+// of the shared buffer; LAST: the outputs go straight to global memory (with the fused
+// epilogue).  Both accesses are coalesced: the first pass reads j + r*N/R, the last
+// pass (NS = N/R) writes k + r*NS, consecutive in the thread index.
+template <int LOGN, int LR, int NS, bool FIRST, bool LAST>
+__device__ __forceinline__ void stockham_pass(double2* s, const double2* __restrict__ tw, int tid,
+                                              const FftArgs& a, const double* rin, double* rout) {
+  constexpr int N = 1 << LOGN, T = N >> 3, R = 1 << LR, NB = 8 >> LR;
+  double2 v[8];
+#pragma unroll
+  for (int q = 0; q < NB; ++q) {
+    const int j = tid + q * T;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (FIRST) v[q * R + r] = load_in(a, rin, j + r * (N / R));
+      else v[q * R + r] = s[pad(j + r * (N / R))];
+    }
+  }
+  if (!FIRST) __syncthreads();
+#pragma unroll
+  for (int q = 0; q < NB; ++q) {
+    const int j = tid + q * T;
+    const int k = j & (NS - 1);
+    double2* b = v + q * R;
+    if (NS > 1) {
+      const double2 w1 = __ldg(tw + (size_t)k * (N / (NS * R)));
+      double2 w = w1;
+#pragma unroll
+      for (int r = 1; r < R; ++r) {
+        b[r] = cmulf(b[r], w);
+        if (r + 1 < R) w = cmulf(w, w1);
+      }
+    }
+    if (LR == 3) dft8(b);
+    else if (LR == 2) dft4(b[0], b[1], b[2], b[3]);
+    else dft2(b[0], b[1]);
+    const int j0 = ((j - k) << LR) + k;   // (j / NS) * NS * R + k
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (LAST) store_out(a, rout, j0 + r * NS, b[r]);
+      else s[pad(j0 + r * NS)] = b[r];
+    }
+  }
+  if (!LAST) __syncthreads();
+}
+
+// GLOBAL_IO: first pass loads from / last pass stores to global memory
+template <int LOGN, int DONE, int NS, bool GLOBAL_IO>
+struct Passes {
+  static __device__ __forceinline__ void run(double2* s, const double2* __restrict__ tw, int tid,
+                                             const FftArgs& a, const double* rin, double* rout) {
+    constexpr int REM = LOGN - DONE;
+    constexpr int LR = REM >= 3 ? 3 : REM;
+    constexpr bool FIRST = GLOBAL_IO && DONE == 0;
+    constexpr bool LAST = GLOBAL_IO && (DONE + LR == LOGN);
+    stockham_pass<LOGN, LR, NS, FIRST, LAST>(s, tw, tid, a, rin, rout);
+    Passes<LOGN, DONE + LR, (NS << LR), GLOBAL_IO>::run(s, tw, tid, a, rin, rout);
+  }
+};
+template <int LOGN, int NS, bool GLOBAL_IO>
+struct Passes<LOGN, LOGN, NS, GLOBAL_IO> {
+  static __device__ __forceinline__ void run(double2*, const double2* __restrict__, int,
+                                             const FftArgs&, const double*, double*) {}
+};
+
+// In-place forward FFT of the padded buffer s (natural order in, natural order
+// out), executed by exactly N/8 threads; tw[j] = exp(-2 pi i j / N).
+template <int LOGN>
+__device__ __forceinline__ void fft_smem_forward(double2* s, const double2* __restrict__ tw, int tid) {
+  FftArgs dummy;
+  Passes<LOGN, 0, 1, false>::run(s, tw, tid, dummy, nullptr, nullptr);
+}
+
 template <int LOGN>
 __global__ void __launch_bounds__((1 << LOGN) / 8 < 32 ? 32 : (1 << LOGN) / 8)
 fft_pow2_kernel(FftArgs a) {
@@ -163,18 +180,11 @@ fft_pow2_kernel(FftArgs a) {
   const int tid = threadIdx.x;
   const double* rin = a.in[blockIdx.y] + (size_t)blockIdx.x * a.in_stride * (a.in_real ? 1 : 2);
   double* rout = a.out[blockIdx.y] + (size_t)blockIdx.x * a.out_stride * (a.out_real ? 1 : 2);
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const int i = tid + q * T;
-    s[pad(i)] = load_in(a, rin, i);
-  }
-  __syncthreads();
-  fft_smem_forward<LOGN>(s, a.tw, tid);
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const int i = tid + q * T;
-    store_out(a, rout, i, s[pad(i)]);
-  }
+  (void)T;
+  // global -> registers -> (smem passes) -> registers -> global: the row never makes
+  // an extra round trip through shared memory, and an in-place call is safe because
+  // every input of the row is in registers/smem before the last pass writes
+  Passes<LOGN, 0, 1, true>::run(s, a.tw, tid, a, rin, rout);
 }
 
 // Rows longer than one CTA's shared memory (N = 16384: 256 KiB): one radix-2
