@@ -72,6 +72,10 @@ __device__ __forceinline__ void gemm_store(double* c, double v0, double v1, doub
 constexpr int kSlabDoubles = BM * LDA_S + BK * LDB_S;
 constexpr int kGemmSmem = 2 * kSlabDoubles * (int)sizeof(double);   // double buffered
 
+// VEC: A rows and B rows are 16-byte aligned with even leading dimensions (the DHT
+// matrices are stored with a padded leading dimension, zeros in the pad), so the
+// global loads are 128-bit.
+template <bool VEC>
 __global__ void __launch_bounds__(kGemmThreads, 2)
 dht_gemm_kernel(GemmArgs p) {
   extern __shared__ double gemm_smem[];
@@ -90,16 +94,34 @@ dht_gemm_kernel(GemmArgs p) {
 
   auto load_slab = [&](uint32_t k0) {
     const uint32_t gr = m0 + a_row;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const uint32_t gk = k0 + a_k + i;
-      ra[i] = (gr < p.M && gk < p.K) ? __ldg(p.A + (size_t)gr * p.lda + gk) : 0.0;
-    }
     const uint32_t gk = k0 + b_row;
+    if (VEC) {
+      // pairs (gk, gk+1): the pad column of A (index >= K, < lda) holds zeros
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const uint32_t gc = n0 + b_col + i;
-      rb[i] = (gk < p.K && gc < p.N) ? __ldg(Bg + (size_t)gk * p.ldb + gc) : 0.0;
+      for (int i = 0; i < 8; i += 2) {
+        const uint32_t ka = k0 + a_k + i;
+        double2 v = make_double2(0.0, 0.0);
+        if (gr < p.M && ka < p.K) v = __ldg(reinterpret_cast<const double2*>(p.A + (size_t)gr * p.lda + ka));
+        ra[i] = v.x; ra[i + 1] = v.y;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; i += 2) {
+        const uint32_t gc = n0 + b_col + i;
+        double2 v = make_double2(0.0, 0.0);
+        if (gk < p.K && gc < p.N) v = __ldg(reinterpret_cast<const double2*>(Bg + (size_t)gk * p.ldb + gc));
+        rb[i] = v.x; rb[i + 1] = v.y;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t ka = k0 + a_k + i;
+        ra[i] = (gr < p.M && ka < p.K) ? __ldg(p.A + (size_t)gr * p.lda + ka) : 0.0;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t gc = n0 + b_col + i;
+        rb[i] = (gk < p.K && gc < p.N) ? __ldg(Bg + (size_t)gk * p.ldb + gc) : 0.0;
+      }
     }
   };
   auto store_slab = [&](int buf) {
@@ -196,12 +218,23 @@ static int dht_launch(const double* A, uint32_t lda, const double* const* Bv, in
   dim3 grid((p.N + BN - 1) / BN, (M + BM - 1) / BM, nbatch);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(dht_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         kGemmSmem);
+    cudaError_t e = cudaFuncSetAttribute(dht_gemm_kernel<false>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(dht_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               kGemmSmem);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  dht_gemm_kernel<<<grid, kGemmThreads, kGemmSmem, (cudaStream_t)stream>>>(p);
+  // 128-bit loads need 16-byte aligned rows: even leading dimensions and aligned bases;
+  // with the pairs (k, k+1) the A rows must have a (zero) pad element when K is odd
+  bool vec = (p.lda % 2 == 0) && (p.ldb % 2 == 0) && (p.N % 2 == 0) &&
+             (reinterpret_cast<uintptr_t>(A) % 16 == 0) && (p.lda > p.K || p.K % 2 == 0);
+  for (int k = 0; k < nbatch && vec; ++k) vec = reinterpret_cast<uintptr_t>(Bv[k]) % 16 == 0;
+  if (vec)
+    dht_gemm_kernel<true><<<grid, kGemmThreads, kGemmSmem, (cudaStream_t)stream>>>(p);
+  else
+    dht_gemm_kernel<false><<<grid, kGemmThreads, kGemmSmem, (cudaStream_t)stream>>>(p);
   CHB_RETURN_LAST_ERROR();
 }
 

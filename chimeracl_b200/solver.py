@@ -31,6 +31,7 @@ class Solver(Grid, Transformer, SolverMethodsCL):
         self.init_transformer()
         self._make_ms_coefficients()
         self.send_args_to_dev()
+        self.pad_operator_matrices()
 
     def push_fields(self):
         self.advance_fields(vecs=['E', 'G', 'J', 'dN0', 'dN1'])

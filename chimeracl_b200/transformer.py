@@ -61,6 +61,25 @@ class Transformer(TransformerMethodsCL):
             comps += [vect + comp for comp in self.Args['vec_comps']]
         self.transform_fields(comps, dir=dir, mode=mode, smooth=smooth)
 
+    def pad_operator_matrices(self):
+        """Re-house the (Nr-1) x (Nr-1) DHT / dDHT matrices in storage with a leading
+        dimension rounded up to a multiple of 8 (zeros in the pad) and expose the same
+        (Nr-1, Nr-1) view under the same DataDev key: rows become 16-byte aligned, which
+        lets the contraction kernel load them 128 bits at a time.  Called after
+        send_args_to_dev()."""
+        import torch
+        from .devarray import DevArray
+        K = self.Args['Nr'] - 1
+        Kp = (K + 7) // 8 * 8
+        for m in range(self.Args['M'] + 1):
+            for name in ('DHT_m', 'DHT_inv_m', 'dDHT_plus_m', 'dDHT_minus_m'):
+                key = name + str(m)
+                if key not in self.DataDev:
+                    continue
+                store = torch.zeros((K, Kp), dtype=torch.float64, device=self.comm.device)
+                store[:, :K] = self.DataDev[key].t
+                self.DataDev[key] = DevArray(store[:, :K])
+
     def _make_spectral_axes(self):
         spectral_axes(self.Args)
 
