@@ -324,6 +324,10 @@ def run_ours(args):
                  "chb_depose_vector": BYTES["depose_vector"],
                  # fused: push_xyz + the whole first sort + depose_vector
                  "chb_push_depose_vector": BYTES["push"] + BYTES["sort"] + BYTES["depose_vector"],
+                 # one pass: both half pushes, the first sort, depose_vector and the
+                 # index/histogram pass (28 B) of the second sort
+                 "chb_push_depose_push_index": 2 * BYTES["push"] + BYTES["sort"] +
+                 BYTES["depose_vector"] + 28,
                  "chb_depose_scalar": BYTES["depose_scalar"], "chb_gather_push": BYTES["gather"]}
     rooflines = {}
     for name, kinfo in kernels.items():
@@ -370,6 +374,7 @@ def run_ours(args):
                   "chb_dht2": "dht_gemm_kernel", "chb_dht_batched": "dht_gemm_kernel",
                   "chb_gather_push": "void gather_push_kernel<1>",
                   "chb_push_depose_vector": "void depose_kernel<1, 1, 1>",
+                  "chb_push_depose_push_index": "void depose_kernel<1, 1, 2>",
                   "chb_depose_scalar": "void depose_kernel<1, 0, 0>",
                   "chb_push_index": "void index_kernel<1>",
                   "chb_psatd_advance": "psatd_kernel",

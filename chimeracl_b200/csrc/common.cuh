@@ -93,6 +93,16 @@ __device__ __forceinline__ void warp_runs(uint32_t key, bool valid, int lane,
   len = next - head_lane;
 }
 
+// One L2 atomic per run of equal cells inside a warp (storage is kept nearly
+// cell-sorted, so a warp of 32 particles spans only a few cells).
+__device__ __forceinline__ void histogram_add(uint32_t cell, bool valid,
+                                              uint32_t* __restrict__ sum_in_cell) {
+  const int lane = threadIdx.x & 31;
+  int head, rank, len;
+  warp_runs(cell, valid, lane, head, rank, len);
+  if (valid && rank == 0) atomicAdd(&sum_in_cell[cell], (uint32_t)len);
+}
+
 // 8-byte asynchronous global -> shared copy (LDGSTS); the copy lands without
 // occupying a register, so many particles' attributes can be in flight per thread.
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {

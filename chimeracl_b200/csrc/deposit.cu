@@ -51,33 +51,48 @@ struct DepArgs {
   double* zw;
   const double* __restrict__ dt_dev;
   uint32_t np_total;
-  uint32_t* exc_count;   // PUSH: number of / sorted positions of the particles that are
-  uint32_t* exc_list;    //       no longer in the cell the traversal order assumes
+  // PUSH: particles that are no longer in the cell the traversal order assumes are
+  // queued as records of their 8 derived values (ax ar wp px py pz e0 e1) and
+  // deposited one by one by depose_push_tail_kernel.  The queue holds one record per
+  // particle (exc_cap == np), so it cannot overflow: a slow path inside the main kernel
+  // would cost registers on its hot loop (measured: 4x the local-memory traffic).
+  uint32_t* exc_count;
+  double* exc_rec;
+  uint32_t exc_cap;
+  // PUSH == 2: the second half push, the cell index and the histogram of the final
+  // coordinates are produced in the same pass (what chb_push_index would do next)
+  uint32_t* indx_in_cell;
+  uint32_t* sum_in_cell;
 };
 
-// Deposit of ONE particle straight to global memory (REDs): used for the few
-// particles whose cell is not the one the traversal order assumes.  Same operation
+__device__ __forceinline__ bool cell_valid(int ix, int ir, const GridVals& g) {
+  return ix > 0 && ix < g.Nx - 2 && ir < g.Nr - 2 && ir >= 0;
+}
+
+// Deposit of ONE particle straight to global memory (REDs), from its derived values
+// ax = (x-xmin)*dx_inv, ar = (r-rmin)*dr_inv, wp = w*g_inv*q, e = (y,z)/r: used for the
+// few particles whose cell is not the one the traversal order assumes.  Same operation
 // order as the reference depose_vector (grid_deposit_m1.cl:268-310).
-template <int M>
-__device__ __noinline__ void deposit_direct(double* const* out, const GridVals& g,
-                                               double xp, double yp, double zp, double jx,
-                                               double jy, double jz, double wp) {
+// (`a` is the kernel parameter block, declared __grid_constant__ so that passing it by
+// reference does not force a per-thread local-memory copy of the whole block.)
+template <int M, class Args>
+__device__ __noinline__ void deposit_derived(const Args& a, const GridVals& g,
+                                                double ax, double ar, double wp, double jx,
+                                                double jy, double jz, double e0, double e1) {
   constexpr int MM = M > 0 ? M : 1;
-  double rp;
-  int ix, ir;
-  cell_coords(xp, yp, zp, g, rp, ix, ir);
-  const double rinv = !(rp > 0.0) ? 0.0 : __drcp_rn(rp);
+  const int ix = floor_to_int(ax), ir = floor_to_int(ar);
+  if (!cell_valid(ix, ir, g)) return;
   double er[MM], ei[MM];
-  er[0] = __dmul_rn(yp, rinv);
-  ei[0] = __dmul_rn(zp, rinv);
+  er[0] = e0;
+  ei[0] = e1;
 #pragma unroll
   for (int m = 1; m < MM; ++m) {
     er[m] = er[m - 1] * er[0] - ei[m - 1] * ei[0];
     ei[m] = er[m - 1] * ei[0] + ei[m - 1] * er[0];
   }
-  double sX1 = __dsub_rn(__dmul_rn(__dsub_rn(xp, g.xmin), g.dx_inv), (double)ix);
+  double sX1 = __dsub_rn(ax, (double)ix);
   double sX0 = __dsub_rn(1.0, sX1);
-  const double sR1 = __dsub_rn(__dmul_rn(__dsub_rn(rp, g.rmin), g.dr_inv), (double)ir);
+  const double sR1 = __dsub_rn(ar, (double)ir);
   const double sR0 = __dsub_rn(1.0, sR1);
   sX0 = __dmul_rn(sX0, wp);
   sX1 = __dmul_rn(sX1, wp);
@@ -90,21 +105,17 @@ __device__ __noinline__ void deposit_direct(double* const* out, const GridVals& 
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       const double pj = __dmul_rn(C[n], jk[k]);
-      red_add_f64(out[k] + node, pj);
+      red_add_f64(a.out[k] + node, pj);
       if (M > 0) {
 #pragma unroll
         for (int m = 0; m < MM; ++m) {
-          double* o = out[(m + 1) * 3 + k] + 2 * node;
+          double* o = a.out[(m + 1) * 3 + k] + 2 * node;
           red_add_f64(o, pj * er[m]);
           red_add_f64(o + 1, pj * ei[m]);
         }
       }
     }
   }
-}
-
-__device__ __forceinline__ bool cell_valid(int ix, int ir, const GridVals& g) {
-  return ix > 0 && ix < g.Nx - 2 && ir < g.Nr - 2 && ir >= 0;
 }
 
 // Threads per CTA: one thread per (cell, component) -- the three current components
@@ -122,15 +133,20 @@ struct DepSmem {
   static constexpr int kBytes = 2 * kSlots * kDepPad * (int)sizeof(double);  // double buffered
 };
 
-// PUSH (J only): the traversal order (sort_indx / cell_offset) is the one of the
-// PREVIOUS sort; every particle is first advanced by the half step (written back),
-// then deposited -- through the cell-ordered fast path if it is still in the cell the
-// order assumes, else (a few per cent) through deposit_direct.  This folds
-// push_coords('half') + sort_parts + depose_currents of pic_loop.py:70-81 into one
-// pass and removes one full sort per step.
-template <int M, bool VEC, bool PUSH = false>
+// PUSH >= 1 (J only): the traversal order (sort_indx / cell_offset) is the one of the
+// PREVIOUS sort; every particle is first advanced by the half step, then deposited --
+// through the cell-ordered fast path if it is still in the cell the order assumes, else
+// (a few per cent) through deposit_derived.  This folds push_coords('half') +
+// sort_parts + depose_currents of pic_loop.py:70-81 into one pass and removes one full
+// sort per step.
+// PUSH == 2: the momenta do not change between the two half pushes of a step
+// (pic_loop.py:70,75), so the second one is applied while the particle is still in
+// registers -- x2 = (x0 + d) + d with the same rounded increment d the two push_xyz
+// launches compute -- and x2's cell index and the cell histogram are produced here as
+// well: the pass also replaces the second push_coords and index_and_sum_in_cell.
+template <int M, bool VEC, int PUSH = 0>
 __global__ void __launch_bounds__(DepShape<VEC>::kThreads, VEC ? 3 : 6)
-depose_kernel(DepArgs<M, VEC> a) {
+depose_kernel(const __grid_constant__ DepArgs<M, VEC> a) {
   static_assert(!PUSH || VEC, "the fused push exists for the current deposit only");
   constexpr int NC = VEC ? 3 : 1;
   constexpr int NT = DepShape<VEC>::kThreads;
@@ -177,6 +193,7 @@ depose_kernel(DepArgs<M, VEC> a) {
   // sorted indices of the particles this thread stages in the NEXT issued batch
   uint32_t sidx[KP];
   uint32_t sprev[PUSH ? KP : 1];   // ... and of the batch in flight (PUSH: write-back)
+  const int lane = threadIdx.x & 31;
   auto load_sidx = [&](uint32_t b0) {
 #pragma unroll
     for (int k = 0; k < KP; ++k) {
@@ -211,8 +228,12 @@ depose_kernel(DepArgs<M, VEC> a) {
   auto convert = [&](uint32_t b0, int buf) {
 #pragma unroll
     for (int k = 0; k < KP; ++k) {
+      // warp-uniform (kDepBatch and NT are multiples of 32)
+      if (!(threadIdx.x - lane + k * NT < kDepBatch)) continue;
       const uint32_t j = b0 + threadIdx.x + k * NT;
-      if (!(j < P1 && threadIdx.x + k * NT < kDepBatch)) continue;
+      const bool valid = j < P1;
+      uint32_t cell2 = 0xffffffffu;
+      if (valid) {
       const int p = pidx((int)(threadIdx.x + k * NT));
       double xp = slot(buf, 0, p), yp = slot(buf, 1, p), zp = slot(buf, 2, p);
       double wp;
@@ -222,10 +243,20 @@ depose_kernel(DepArgs<M, VEC> a) {
         // half push, same arithmetic as push_xyz (particles_generic.cl:142-151)
         const uint32_t s = sprev[k];
         const double dt_g = __dmul_rn(dt, slot(buf, 7, p));
-        xp = __dadd_rn(xp, __dmul_rn(slot(buf, 3, p), dt_g));
-        yp = __dadd_rn(yp, __dmul_rn(slot(buf, 4, p), dt_g));
-        zp = __dadd_rn(zp, __dmul_rn(slot(buf, 5, p), dt_g));
-        a.xw[s] = xp; a.yw[s] = yp; a.zw[s] = zp;
+        const double ddx = __dmul_rn(slot(buf, 3, p), dt_g);
+        const double ddy = __dmul_rn(slot(buf, 4, p), dt_g);
+        const double ddz = __dmul_rn(slot(buf, 5, p), dt_g);
+        xp = __dadd_rn(xp, ddx);
+        yp = __dadd_rn(yp, ddy);
+        zp = __dadd_rn(zp, ddz);
+        if (PUSH == 2) {
+          const double x2 = __dadd_rn(xp, ddx), y2 = __dadd_rn(yp, ddy), z2 = __dadd_rn(zp, ddz);
+          a.xw[s] = x2; a.yw[s] = y2; a.zw[s] = z2;
+          cell2 = cell_index(x2, y2, z2, g);
+          a.indx_in_cell[s] = cell2;
+        } else {
+          a.xw[s] = xp; a.yw[s] = yp; a.zw[s] = zp;
+        }
       }
       const double rp = __dsqrt_rn(__dadd_rn(__dmul_rn(yp, yp), __dmul_rn(zp, zp)));
       slot(buf, 0, p) = __dmul_rn(__dsub_rn(xp, g.xmin), g.dx_inv);
@@ -238,6 +269,8 @@ depose_kernel(DepArgs<M, VEC> a) {
         slot(buf, SL_E0, p) = __dmul_rn(yp, rinv);
         slot(buf, SL_E1, p) = __dmul_rn(zp, rinv);
       }
+      }
+      if (PUSH == 2) histogram_add(cell2, valid, a.sum_in_cell);
     }
   };
 
@@ -268,7 +301,14 @@ depose_kernel(DepArgs<M, VEC> a) {
         // floor(ax) == ix  <=>  0 <= ax - ix < 1 (the subtraction is exact): a particle
         // that left this cell during the push goes to the exception list instead
         if (!(sX1 >= 0.0 && sX1 < 1.0 && sR1 >= 0.0 && sR1 < 1.0)) {
-          if (comp == 0) a.exc_list[atomicAdd(a.exc_count, 1u)] = j;
+          if (comp == 0) {
+            const uint32_t e = atomicAdd(a.exc_count, 1u);
+            if (e < a.exc_cap) {
+              double* rec = a.exc_rec + (size_t)e * 8;
+#pragma unroll
+              for (int sl = 0; sl < 8; ++sl) rec[sl] = slot(buf, sl, p);
+            }
+          }
           continue;
         }
       }
@@ -324,10 +364,11 @@ depose_kernel(DepArgs<M, VEC> a) {
 }
 
 // PUSH: particles beyond the last real cell of the previous sort (its trash bin) are
-// pushed too and, should they have re-entered the box, deposited directly.
-template <int M>
+// pushed too and, should they have re-entered the box, deposited directly; then the
+// queued cell changers are deposited from their records.
+template <int M, int PUSH>
 __global__ void __launch_bounds__(256)
-depose_push_tail_kernel(DepArgs<M, true> a) {
+depose_push_tail_kernel(const __grid_constant__ DepArgs<M, true> a) {
   const GridVals g = load_geom(a.geom);
   const double dt = __ldg(a.dt_dev);
   const double q = (double)a.charge;
@@ -337,32 +378,34 @@ depose_push_tail_kernel(DepArgs<M, true> a) {
     const uint32_t s = __ldg(a.sort_indx + j);
     const double ux = a.px[s], uy = a.py[s], uz = a.pz[s], gi = a.g_inv[s];
     const double dt_g = __dmul_rn(dt, gi);
-    const double xp = __dadd_rn(a.xw[s], __dmul_rn(ux, dt_g));
-    const double yp = __dadd_rn(a.yw[s], __dmul_rn(uy, dt_g));
-    const double zp = __dadd_rn(a.zw[s], __dmul_rn(uz, dt_g));
-    a.xw[s] = xp; a.yw[s] = yp; a.zw[s] = zp;
-    double r_;
-    int ix, ir;
-    cell_coords(xp, yp, zp, g, r_, ix, ir);
-    if (cell_valid(ix, ir, g))
-      deposit_direct<M>(a.out, g, xp, yp, zp, ux, uy, uz,
-                        __dmul_rn(__dmul_rn(a.w[s], gi), q));
+    const double ddx = __dmul_rn(ux, dt_g), ddy = __dmul_rn(uy, dt_g), ddz = __dmul_rn(uz, dt_g);
+    const double xp = __dadd_rn(a.xw[s], ddx);
+    const double yp = __dadd_rn(a.yw[s], ddy);
+    const double zp = __dadd_rn(a.zw[s], ddz);
+    if (PUSH == 2) {
+      const double x2 = __dadd_rn(xp, ddx), y2 = __dadd_rn(yp, ddy), z2 = __dadd_rn(zp, ddz);
+      a.xw[s] = x2; a.yw[s] = y2; a.zw[s] = z2;
+      const uint32_t cell2 = cell_index(x2, y2, z2, g);
+      a.indx_in_cell[s] = cell2;
+      atomicAdd(&a.sum_in_cell[cell2], 1u);
+    } else {
+      a.xw[s] = xp; a.yw[s] = yp; a.zw[s] = zp;
+    }
+    const double rp = __dsqrt_rn(__dadd_rn(__dmul_rn(yp, yp), __dmul_rn(zp, zp)));
+    const double rinv = !(rp > 0.0) ? 0.0 : __drcp_rn(rp);
+    deposit_derived<M>(a, g, __dmul_rn(__dsub_rn(xp, g.xmin), g.dx_inv),
+                       __dmul_rn(__dsub_rn(rp, g.rmin), g.dr_inv),
+                       __dmul_rn(__dmul_rn(a.w[s], gi), q), ux, uy, uz, __dmul_rn(yp, rinv),
+                       __dmul_rn(zp, rinv));
   }
-  // particles (already pushed) that changed cell: deposit at their new position
-  const uint32_t nexc = *a.exc_count;
+  const uint32_t nexc = min(*a.exc_count, a.exc_cap);
   for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < nexc; e += gridDim.x * blockDim.x) {
-    const uint32_t s = __ldg(a.sort_indx + a.exc_list[e]);
-    const double xp = a.xw[s], yp = a.yw[s], zp = a.zw[s];
-    double r_;
-    int ix, ir;
-    cell_coords(xp, yp, zp, g, r_, ix, ir);
-    if (cell_valid(ix, ir, g))
-      deposit_direct<M>(a.out, g, xp, yp, zp, a.px[s], a.py[s], a.pz[s],
-                        __dmul_rn(__dmul_rn(a.w[s], a.g_inv[s]), q));
+    const double* rec = a.exc_rec + (size_t)e * 8;
+    deposit_derived<M>(a, g, rec[0], rec[1], rec[2], rec[3], rec[4], rec[5], rec[6], rec[7]);
   }
 }
 
-template <int M, bool VEC, bool PUSH = false>
+template <int M, bool VEC, int PUSH = 0>
 static int launch_depose(DepArgs<M, VEC>& a, cudaStream_t st) {
   uint32_t grid = (a.ncells + kDepCells - 1) / kDepCells;
   constexpr int smem = DepSmem<M, VEC>::kBytes;
@@ -441,7 +484,8 @@ int chb_depose_scalar(int M, const uint32_t* sort_indx, const double* x, const d
   {                                                                             \
     DepArgs<MM, false> a{sort_indx, x, y, z, nullptr, nullptr, nullptr, nullptr, w, \
                          cell_offset, {}, g, charge, (Nx - 1) * (Nr - 1),       \
-                         nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr}; \
+                         nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, 0,   \
+                         nullptr, nullptr};                                     \
     for (int k = 0; k < MM + 1; ++k) a.out[k] = rho_host[k];                    \
     return launch_depose<MM, false>(a, st);                                     \
   }
@@ -466,7 +510,8 @@ int chb_depose_vector(int M, const uint32_t* sort_indx, const double* x, const d
   {                                                                             \
     DepArgs<MM, true> a{sort_indx, x, y, z, px, py, pz, g_inv, w, cell_offset,  \
                         {}, g, charge, (Nx - 1) * (Nr - 1),                     \
-                        nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr}; \
+                        nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, 0,   \
+                        nullptr, nullptr};                                      \
     for (int k = 0; k < 3 * (MM + 1); ++k) a.out[k] = j_host[k];                \
     return launch_depose<MM, true>(a, st);                                      \
   }
@@ -478,6 +523,56 @@ int chb_depose_vector(int M, const uint32_t* sort_indx, const double* x, const d
 #undef CHB_GO
 }
 
+size_t chb_push_depose_workspace_bytes(uint32_t np) {
+  // counter (16 bytes) + one record of 8 doubles per particle (worst case: every
+  // particle changed cell)
+  return 16 + (size_t)np * 8 * sizeof(double);
+}
+
+static int push_depose(int M, int push, const uint32_t* sort_indx, double* x, double* y,
+                       double* z, const double* px, const double* py, const double* pz,
+                       const double* g_inv, const double* w, const uint32_t* cell_offset,
+                       const double* dt_dev, uint32_t np, int charge, uint32_t Nx, uint32_t Nr,
+                       const double* xmin, const double* dx_inv, const double* rmin,
+                       const double* dr_inv, double* const* j_host, uint32_t* indx_in_cell,
+                       uint32_t* sum_in_cell, void* workspace, size_t workspace_bytes,
+                       void* stream) {
+  if (M < 0 || M >= CHB_MAX_MODES || Nx < 3 || Nr < 3) return CHB_ERR_ARG;
+  if (np == 0) return CHB_OK;
+  if (workspace_bytes < chb_push_depose_workspace_bytes(np) ||
+      (reinterpret_cast<uintptr_t>(workspace) & 7u) != 0)
+    return CHB_ERR_WORKSPACE;
+  GridGeom g{xmin, dx_inv, rmin, dr_inv, Nx, Nr};
+  cudaStream_t st = (cudaStream_t)stream;
+  uint32_t* exc_count = (uint32_t*)workspace;
+  double* exc_rec = (double*)((char*)workspace + 16);
+  size_t cap = (workspace_bytes - 16) / (8 * sizeof(double));
+  if (cap > 0xffffffffull) cap = 0xffffffffull;
+  {
+    cudaError_t e = cudaMemsetAsync(exc_count, 0, sizeof(uint32_t), st);
+    if (e != cudaSuccess) return (int)e;
+  }
+#define CHB_GO2(MM, PP)                                                         \
+  {                                                                             \
+    DepArgs<MM, true> a{sort_indx, x, y, z, px, py, pz, g_inv, w, cell_offset,  \
+                        {}, g, charge, (Nx - 1) * (Nr - 1), x, y, z, dt_dev, np,  \
+                        exc_count, exc_rec, (uint32_t)cap, indx_in_cell, sum_in_cell}; \
+    for (int k = 0; k < 3 * (MM + 1); ++k) a.out[k] = j_host[k];                \
+    int rc = launch_depose<MM, true, PP>(a, st);                                \
+    if (rc) return rc;                                                          \
+    depose_push_tail_kernel<MM, PP><<<kSMs, 256, 0, st>>>(a);                   \
+    CHB_RETURN_LAST_ERROR();                                                    \
+  }
+#define CHB_GO(MM) { if (push == 2) CHB_GO2(MM, 2) else CHB_GO2(MM, 1) }
+  switch (M) {
+    case 0: CHB_GO(0)
+    case 1: CHB_GO(1)
+    default: CHB_GO(2)
+  }
+#undef CHB_GO
+#undef CHB_GO2
+}
+
 int chb_push_depose_vector(int M, const uint32_t* sort_indx, double* x, double* y, double* z,
                            const double* px, const double* py, const double* pz,
                            const double* g_inv, const double* w,
@@ -486,34 +581,24 @@ int chb_push_depose_vector(int M, const uint32_t* sort_indx, double* x, double* 
                            const double* dx_inv, const double* rmin, const double* dr_inv,
                            double* const* j_host, void* workspace, size_t workspace_bytes,
                            void* stream) {
-  if (M < 0 || M >= CHB_MAX_MODES || Nx < 3 || Nr < 3) return CHB_ERR_ARG;
-  if (np == 0) return CHB_OK;
-  if (workspace_bytes < ((size_t)np + 1) * sizeof(uint32_t)) return CHB_ERR_WORKSPACE;
-  GridGeom g{xmin, dx_inv, rmin, dr_inv, Nx, Nr};
-  cudaStream_t st = (cudaStream_t)stream;
-  uint32_t* exc_count = (uint32_t*)workspace;
-  uint32_t* exc_list = exc_count + 1;
-  {
-    cudaError_t e = cudaMemsetAsync(exc_count, 0, sizeof(uint32_t), st);
-    if (e != cudaSuccess) return (int)e;
-  }
-#define CHB_GO(MM)                                                              \
-  {                                                                             \
-    DepArgs<MM, true> a{sort_indx, x, y, z, px, py, pz, g_inv, w, cell_offset,  \
-                        {}, g, charge, (Nx - 1) * (Nr - 1), x, y, z, dt_dev, np,  \
-                        exc_count, exc_list};                                   \
-    for (int k = 0; k < 3 * (MM + 1); ++k) a.out[k] = j_host[k];                \
-    int rc = launch_depose<MM, true, true>(a, st);                              \
-    if (rc) return rc;                                                          \
-    depose_push_tail_kernel<MM><<<kSMs, 256, 0, st>>>(a);                       \
-    CHB_RETURN_LAST_ERROR();                                                    \
-  }
-  switch (M) {
-    case 0: CHB_GO(0)
-    case 1: CHB_GO(1)
-    default: CHB_GO(2)
-  }
-#undef CHB_GO
+  return push_depose(M, 1, sort_indx, x, y, z, px, py, pz, g_inv, w, cell_offset, dt_dev, np,
+                     charge, Nx, Nr, xmin, dx_inv, rmin, dr_inv, j_host, nullptr, nullptr,
+                     workspace, workspace_bytes, stream);
+}
+
+int chb_push_depose_push_index(int M, const uint32_t* sort_indx, double* x, double* y,
+                               double* z, const double* px, const double* py,
+                               const double* pz, const double* g_inv, const double* w,
+                               const uint32_t* cell_offset, const double* dt_dev, uint32_t np,
+                               int charge, uint32_t Nx, uint32_t Nr, const double* xmin,
+                               const double* dx_inv, const double* rmin, const double* dr_inv,
+                               double* const* j_host, uint32_t* indx_in_cell,
+                               uint32_t* sum_in_cell, void* workspace, size_t workspace_bytes,
+                               void* stream) {
+  if (!indx_in_cell || !sum_in_cell) return CHB_ERR_ARG;
+  return push_depose(M, 2, sort_indx, x, y, z, px, py, pz, g_inv, w, cell_offset, dt_dev, np,
+                     charge, Nx, Nr, xmin, dx_inv, rmin, dr_inv, j_host, indx_in_cell,
+                     sum_in_cell, workspace, workspace_bytes, stream);
 }
 
 int chb_postproc_depose(double* const* fld_host, const int* is_complex_host, int nfld,

@@ -65,16 +65,6 @@ push_xyz_kernel(double* __restrict__ x, double* __restrict__ y, double* __restri
 }
 
 // ------------------------------------------------------------------ index + histogram
-// One L2 atomic per run of equal cells inside a warp (storage is kept nearly
-// cell-sorted, so a warp of 32 particles spans only a few cells).
-__device__ __forceinline__ void histogram_add(uint32_t cell, bool valid,
-                                              uint32_t* __restrict__ sum_in_cell) {
-  const int lane = threadIdx.x & 31;
-  int head, rank, len;
-  warp_runs(cell, valid, lane, head, rank, len);
-  if (valid && rank == 0) atomicAdd(&sum_in_cell[cell], (uint32_t)len);
-}
-
 template <bool PUSH>
 __global__ void __launch_bounds__(kBlock)
 index_kernel(double* __restrict__ x, double* __restrict__ y, double* __restrict__ z,

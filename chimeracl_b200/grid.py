@@ -85,10 +85,13 @@ class Grid(GridMethodsCL):
                 continue
             push_dt = None
             if push_mode is not None:
-                # fused push_coords(push_mode) + sort_parts + deposit for this species
-                push_dt = 'dt_2' if push_mode == 'half' else 'dt'
+                # fused push_coords + sort_parts + deposit for this species; with
+                # 'half+half' also the second half push and the cell index of the
+                # following sort_parts (pic_loop.py:70-76 in one pass)
+                push_dt = 'dt' if push_mode == 'full' else 'dt_2'
             self.depose_vector(parts, ['p' + comp for comp in comps], ['g_inv', 'w'], 'J',
-                               charge=parts.Args['charge'], push_dt=push_dt)
+                               charge=parts.Args['charge'], push_dt=push_dt,
+                               second_push_index=(push_mode == 'half+half'))
         if defer:
             # the sum over ranks runs while the caller goes on (second push + sort);
             # finish_currents() must be called before J is used

@@ -45,7 +45,8 @@ class GridMethodsCL(GenericMethodsCL):
                    P['y'].ptr, P['z'].ptr, P[src_scalar].ptr, P['cell_offset'].ptr,
                    int(np.int8(charge)), *self._geom(), flds)
 
-    def depose_vector(self, parts, vec, factors, vec_fld, charge, push_dt=None):
+    def depose_vector(self, parts, vec, factors, vec_fld, charge, push_dt=None,
+                      second_push_index=False):
         if parts.Args['Np'] <= 0:
             return
         P = parts.DataDev
@@ -53,6 +54,19 @@ class GridMethodsCL(GenericMethodsCL):
         for m in range(self.Args['M'] + 1):
             for comp in self.Args['vec_comps']:
                 flds.append(self.DataDev[vec_fld + comp + '_m' + str(m)].ptr)
+        if push_dt is not None and second_push_index:
+            # one pass: push, deposit, second push, cell index + histogram
+            # (chb_push_depose_push_index); the caller finishes the sort
+            indx, hist = parts.prepare_index(self)
+            self._call('chb_push_depose_push_index', int(self.Args['M']), P['sort_indx'].ptr,
+                       P['x'].ptr, P['y'].ptr, P['z'].ptr, P[vec[0]].ptr, P[vec[1]].ptr,
+                       P[vec[2]].ptr, P[factors[0]].ptr, P[factors[1]].ptr,
+                       P['cell_offset'].ptr, P[push_dt].ptr, int(parts.Args['Np']),
+                       int(np.int8(charge)), *self._geom(), _lib.ptr_array(flds),
+                       indx.ptr, hist.ptr, *parts.exception_workspace())
+            parts.flag_sorted = False
+            parts._index_prefilled = True
+            return
         if push_dt is not None:
             # coordinates advance by push_dt ('dt_2' | 'dt') inside the deposit; the
             # previous sort only provides the traversal order (chb_push_depose_vector)

@@ -52,13 +52,14 @@ class ParticleMethodsCL(GenericMethodsCL):
                 and self.DataDev['sort_indx'].size == self.Args['Np'])
 
     def exception_workspace(self):
-        """(pointer, bytes) of the (Np+1) x u32 scratch chb_push_depose_vector needs."""
-        n = int(self.Args['Np']) + 1
-        ws = self._buf('exc_ws', n, np.uint32)
-        return ws.ptr, n * 4
+        """(pointer, bytes) of the scratch chb_push_depose_vector / _push_index need."""
+        nbytes = int(self._lib.chb_push_depose_workspace_bytes(int(self.Args['Np'])))
+        ws = self._buf('exc_ws', (nbytes + 7) // 8, np.double)
+        return ws.ptr, nbytes
 
     def add_new_particles(self, source=None):
         self._order_np = -1
+        self._index_prefilled = False
         DataSrc = self.DataDev if source is None else source.DataDev
         for arg in self._attr_names():
             self.DataDev[arg] = DevArray(torch.cat((self.DataDev[arg].t,
@@ -199,12 +200,28 @@ class ParticleMethodsCL(GenericMethodsCL):
             self.push_coords(mode)
             self.sort_parts(grid)
             return
+        if getattr(self, '_index_prefilled', False):
+            # the push happened inside chb_push_depose_push_index
+            self.flag_sorted = False
+            self.sort_parts(grid)
+            return
         self._pending_push = 'dt_2' if mode == 'half' else 'dt'
         self.flag_sorted = False
         try:
             self.sort_parts(grid)
         finally:
             self._pending_push = None
+
+    def prepare_index(self, grid):
+        """Allocate (persistent workspaces) and zero the products of the cell index pass;
+        returns (indx_in_cell, sum_in_cell)."""
+        D = self.DataDev
+        Np = int(self.Args['Np'])
+        nbins = int(grid.Args['Nxm1Nrm1']) + 1
+        D['indx_in_cell'] = self._buf('indx_in_cell', Np, np.uint32)
+        D['sum_in_cell'] = self._buf('sum_in_cell', nbins, np.uint32)
+        D['sum_in_cell'].t.zero_()
+        return D['indx_in_cell'], D['sum_in_cell']
 
     def index_sort(self, grid):
         lib, st = self._lib, self._stream
@@ -213,20 +230,24 @@ class ParticleMethodsCL(GenericMethodsCL):
         nbins = int(grid.Args['Nxm1Nrm1']) + 1
         Nx, Nr = int(grid.Args['Nx']), int(grid.Args['Nr'])
 
+        # chb_push_depose_push_index already pushed the coordinates and filled
+        # indx_in_cell / sum_in_cell (PIC_loop's one-pass particle side)
+        prefilled, self._index_prefilled = getattr(self, '_index_prefilled', False), False
         self._order_np, self._order_grid = Np, grid
-        D['indx_in_cell'] = self._buf('indx_in_cell', Np, np.uint32)
-        D['sum_in_cell'] = self._buf('sum_in_cell', nbins, np.uint32)
+        if not prefilled:
+            self.prepare_index(grid)
         D['cell_offset'] = self._buf('cell_offset', nbins + 1, np.uint32)
         D['sort_indx'] = self._buf('sort_indx', Np, np.uint32)
         cursor = self._buf('cursor', nbins, np.uint32)
         if 'Np_stay_dev' not in D:
             D['Np_stay_dev'] = DevArray.zeros(1, np.uint32, self.comm.device)
             self._np_stay_host = torch.zeros(1, dtype=torch.int32).pin_memory()
-        D['sum_in_cell'].t.zero_()
 
         geom = (G['Xmin'].ptr, G['dx_inv'].ptr, G['Rmin'].ptr, G['dr_inv'].ptr)
         which_dt, self._pending_push = self._pending_push, None
-        if which_dt is not None:
+        if prefilled:
+            pass
+        elif which_dt is not None:
             _lib.check(lib.chb_push_index(
                 D['x'].ptr, D['y'].ptr, D['z'].ptr, D['px'].ptr, D['py'].ptr, D['pz'].ptr,
                 D['g_inv'].ptr, D[which_dt].ptr, D['indx_in_cell'].ptr, D['sum_in_cell'].ptr,

@@ -62,7 +62,10 @@ class PIC_loop:
 
         # first half push + sort + current deposit.  When every mobile species still
         # has the previous step's sort as a valid traversal order, the three are ONE
-        # pass (chb_push_depose_vector) and the first sort of the step is not needed.
+        # pass and the first sort of the step is not needed; the same pass applies the
+        # second half push (the momenta do not change in between) and computes the cell
+        # indices of the second sort (chb_push_depose_push_index), which then only has
+        # its scan + scatter left.
         fuse_first = self.fuse_push_sort and len(self.solvers) == 1 and \
             hasattr(self.mainsolver, 'finish_currents') and self._can_fuse_first_half()
         if not fuse_first:
@@ -71,7 +74,8 @@ class PIC_loop:
         self.timer_start()
         for solver in self.solvers:
             if fuse_first:
-                solver.depose_currents(species=self.species, defer=True, push_mode='half')
+                solver.depose_currents(species=self.species, defer=True,
+                                       push_mode='half+half')
             elif hasattr(solver, 'finish_currents'):
                 solver.depose_currents(species=self.species, defer=True)
             else:

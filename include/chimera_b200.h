@@ -118,7 +118,9 @@ int chb_depose_vector(int M, const uint32_t* sort_indx, const double* x, const d
  * particles still in the cell that order assumes take the cell-ordered fast path, the
  * others (and the previous trash bin) are deposited one by one.  Same sums as
  * chb_push_xyz -> sort -> chb_depose_vector up to summation order; np = all particles;
- * workspace: (np + 1) * 4 bytes (list of the particles that changed cell). */
+ * workspace (8-byte aligned): chb_push_depose_workspace_bytes(np) bytes (queue of the
+ * cell changers, sized for the worst case; CHB_ERR_WORKSPACE if smaller). */
+size_t chb_push_depose_workspace_bytes(uint32_t np);
 int chb_push_depose_vector(int M, const uint32_t* sort_indx, double* x, double* y, double* z,
                            const double* px, const double* py, const double* pz,
                            const double* g_inv, const double* w,
@@ -127,6 +129,24 @@ int chb_push_depose_vector(int M, const uint32_t* sort_indx, double* x, double* 
                            const double* dx_inv, const double* rmin, const double* dr_inv,
                            double* const* j_host, void* workspace, size_t workspace_bytes,
                            void* stream);
+
+/* The whole particle side of pic_loop.py:70-76 in ONE pass: push_coords('half') +
+ * sort_parts + depose_currents as chb_push_depose_vector, then -- the momenta being
+ * unchanged between the two half pushes of a step -- the second push_coords('half')
+ * (x2 = (x0 + d) + d with the same rounded d = p*(dt*g_inv) both chb_push_xyz calls
+ * would use, so x, y, z are bit-identical) and the index_and_sum_in_cell of the second
+ * sort_parts: indx_in_cell[np] and sum_in_cell (zeroed by the caller, (Nx-1)*(Nr-1)+1
+ * bins) are those chb_push_index would produce.  The caller continues with
+ * chb_cell_offsets and chb_sort_scatter_stable. */
+int chb_push_depose_push_index(int M, const uint32_t* sort_indx, double* x, double* y,
+                               double* z, const double* px, const double* py,
+                               const double* pz, const double* g_inv, const double* w,
+                               const uint32_t* cell_offset, const double* dt_dev, uint32_t np,
+                               int charge, uint32_t Nx, uint32_t Nr, const double* xmin,
+                               const double* dx_inv, const double* rmin, const double* dr_inv,
+                               double* const* j_host, uint32_t* indx_in_cell,
+                               uint32_t* sum_in_cell, void* workspace, size_t workspace_bytes,
+                               void* stream);
 
 /* row1 -= row0, then arr[ir,:] *= dV_inv[ir], for nfld arrays in one launch
  * (is_complex_host[k] != 0 for complex arrays).  Replaces treat_axis_{d,c} and

@@ -517,3 +517,49 @@ def test_fused_push_deposit_equals_push_sort_deposit(comm, M):
     P2.sort_parts(S2)
     check_equal = [np.array_equal(P1.DataDev[k].get(), P2.DataDev[k].get()) for k in INT_KEYS]
     assert all(check_equal)
+
+
+@pytest.mark.parametrize("M", [0, 1, 2])
+def test_one_pass_particle_side_equals_reference_sequence(comm, M):
+    """chb_push_depose_push_index (half push + J deposit + second half push + cell
+    index / histogram in one pass, then scan + scatter) against the reference sequence
+    pic_loop.py:70-76: push_coords, sort_parts, depose_currents, push_coords,
+    sort_parts.  Coordinates and every sort product bit-exact, J <= 1e-12; fast
+    particles so that the cell-changer queue, its overflow path and the trash bin
+    are all exercised."""
+    from chimeracl_b200.solver import Solver
+    from chimeracl_b200.particles import Particles
+    cfg = {"Xmin": -1.0, "Xmax": 1.0, "Nx": 48, "Rmin": 0.0, "Rmax": 1.0, "Nr": 24, "M": M}
+    S1, S2 = Solver(dict(cfg), comm), Solver(dict(cfg), comm)
+    rng = np.random.default_rng(78 + M)
+    n = 150001
+    arrays = {"x": rng.uniform(-1.15, 1.15, n), "y": rng.normal(0, 0.45, n),
+              "z": rng.normal(0, 0.45, n), "px": rng.normal(0, 2, n), "py": rng.normal(0, 2, n),
+              "pz": rng.normal(0, 2, n), "w": rng.uniform(0.5, 1.5, n)}
+    arrays["y"][:7] = 0.0
+    arrays["z"][:7] = 0.0                     # on-axis particles: guarded 1/r
+    arrays["g_inv"] = 1 / np.sqrt(1 + arrays["px"] ** 2 + arrays["py"] ** 2 + arrays["pz"] ** 2)
+    pcfg = {"charge": -1, "dt": 0.08}
+    P1, P2 = Particles(dict(pcfg), comm), Particles(dict(pcfg), comm)
+    for P, S in ((P1, S1), (P2, S2)):
+        set_particles(P, arrays)
+        P.sort_parts(S)                       # the "previous step's" sort
+    # reference sequence
+    P1.push_coords("half")
+    P1.sort_parts(S1)
+    S1.depose_currents([P1])
+    P1.push_coords("half")
+    P1.sort_parts(S1)
+    # one pass + scan/scatter
+    S2.depose_currents([P2], push_mode="half+half")
+    assert P2.flag_sorted is False and P2._index_prefilled is True
+    P2.push_and_sort(S2, mode="half")
+    assert P2._index_prefilled is False and P2.flag_sorted is True
+    for k in ("x", "y", "z"):
+        assert np.array_equal(P1.DataDev[k].get(), P2.DataDev[k].get()), k
+    for k in INT_KEYS:
+        assert np.array_equal(P1.DataDev[k].get(), P2.DataDev[k].get()), k
+    assert int(P1.Args["Np_stay"]) == int(P2.Args["Np_stay"])
+    for k in S1.DataDev:
+        if k.startswith(("Jx_m", "Jy_m", "Jz_m")):
+            assert rel_err(S2.DataDev[k].get(), S1.DataDev[k].get()) < 1e-12, k
