@@ -15,6 +15,7 @@
 // current one is multiplied.  Optional fused epilogue: complex alpha and
 // accumulate-into-C, which folds the reference's zpaxz/append_c2c passes
 // (kernels/generic.cl:18-45) into the contraction.
+#include <cstdlib>
 #include "common.cuh"
 #include "../../include/chimera_b200.h"
 
@@ -184,6 +185,194 @@ dht_gemm_kernel(GemmArgs p) {
   }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Wide-tile variant: one 16-warp CTA per SM, 128 x (16*NT) tile, warp tile 16 x (8*NT)
+// (a single warp cannot issue DMMAs back to back at the pipe's rate -- measured with
+// tools/exp/fp64_pipes.cu: one warp per scheduler reaches half of it -- so four warps
+// per scheduler keep the pipe fed while others load fragments or wait), operands
+// brought in by a 3-stage 16-byte cp.async pipeline of 32-deep k-slabs (zero-filled at the
+// K / N edges), one barrier per slab.  The tile width is chosen per launch so that the number of tiles is
+// (just under) a multiple of the 148 SMs: for Nx = 4096 a 112-wide tile gives exactly 148
+// (real) / 296 (complex) tiles per contraction, i.e. whole waves, where the 128 x 64 tiles
+// above ran 1.73 waves.  Needs 16-byte aligned operands (see dht_launch).
+constexpr int kWideStages = 3;
+constexpr int kWideThreads = 512;      // 16 warps: 8 (M) x 2 (N)
+constexpr int WBK = 32;                // k-slab of the wide kernel
+constexpr int WLDA = WBK + 4;          // 36: (g*36 + t) mod 16 distinct over a half warp
+
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gmem_src, bool valid) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int n = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem_src), "r"(n)
+               : "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+template <int NT>
+struct WideShape {
+  static constexpr int kBN = 16 * NT;
+  static constexpr int kLdb = kBN + 4;                 // (t*kLdb + g) mod 16 distinct (kBN % 16 == 0)
+  static constexpr int kStageDoubles = BM * WLDA + WBK * kLdb;
+  static constexpr int kSmem = kWideStages * kStageDoubles * (int)sizeof(double);
+};
+
+template <int NT>
+__global__ void __launch_bounds__(kWideThreads, 1)
+dht_gemm_wide_kernel(const __grid_constant__ GemmArgs p) {
+  using S = WideShape<NT>;
+  constexpr int BNW = S::kBN;
+  extern __shared__ __align__(16) double gemm_smem[];
+  const double* __restrict__ Bg = p.Bv[blockIdx.z];
+  double* __restrict__ Cg = p.Cv[blockIdx.z];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm = warp >> 1, wn = warp & 1;          // wm: 0..7
+  const uint32_t m0 = blockIdx.y * BM, n0 = blockIdx.x * BNW;
+
+  // cp.async assignment, fixed per thread for the whole k loop: the A slab is 128 rows x
+  // 16 chunks of 16 bytes, the B slab 32 rows x BNW/2 chunks; only the k offset moves
+  constexpr int kAPer = BM * (WBK / 2) / kWideThreads;                     // 4
+  constexpr int kBChunks = WBK * (BNW / 2);
+  constexpr int kBPer = (kBChunks + kWideThreads - 1) / kWideThreads;      // 4 (NT = 7: 3.5)
+  const double* a_src[kAPer];
+  uint32_t a_dst[kAPer], a_k[kAPer];
+  bool a_ok[kAPer];
+#pragma unroll
+  for (int i = 0; i < kAPer; ++i) {
+    const int c = tid + i * kWideThreads;
+    const int row = c >> 4, kc = (c & 15) * 2;
+    a_ok[i] = m0 + row < p.M;
+    a_src[i] = p.A + (size_t)(a_ok[i] ? m0 + row : 0) * p.lda + kc;
+    a_dst[i] = row * WLDA + kc;
+    a_k[i] = kc;
+  }
+  const double* b_src[kBPer];
+  uint32_t b_dst[kBPer], b_k[kBPer];
+  bool b_ok[kBPer];
+#pragma unroll
+  for (int i = 0; i < kBPer; ++i) {
+    const int c = tid + i * kWideThreads;
+    const int row = c / (BNW / 2), cc = (c - row * (BNW / 2)) * 2;
+    b_ok[i] = c < kBChunks && n0 + cc < p.N;
+    b_src[i] = Bg + (size_t)row * p.ldb + (b_ok[i] ? n0 + cc : 0);
+    b_dst[i] = BM * WLDA + row * S::kLdb + cc;
+    b_k[i] = row;
+  }
+  const size_t b_step = (size_t)WBK * p.ldb;
+
+  // slabs are issued strictly in order, so the sources just advance
+  auto issue = [&](uint32_t k0, int stage) {
+    double* st = gemm_smem + stage * S::kStageDoubles;
+#pragma unroll
+    for (int i = 0; i < kAPer; ++i) {
+      const bool ok = a_ok[i] && k0 + a_k[i] < p.lda;      // pad columns [K, lda) hold zeros
+      cp_async16_zfill(st + a_dst[i], ok ? a_src[i] : p.A, ok);
+      a_src[i] += WBK;
+    }
+#pragma unroll
+    for (int i = 0; i < kBPer; ++i) {
+      if (kBChunks % kWideThreads != 0 && i == kBPer - 1 && tid + i * kWideThreads >= kBChunks)
+        break;
+      const bool ok = b_ok[i] && k0 + b_k[i] < p.K;
+      cp_async16_zfill(st + b_dst[i], ok ? b_src[i] : Bg, ok);
+      b_src[i] += b_step;
+    }
+  };
+
+  double acc[2][NT][2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  const uint32_t nslab = (p.K + WBK - 1) / WBK;
+#pragma unroll
+  for (int s = 0; s < kWideStages - 1; ++s) {
+    if ((uint32_t)s < nslab) issue(s * WBK, s);
+    cp_async_commit();
+  }
+  int stage = 0;
+  for (uint32_t it = 0; it < nslab; ++it) {
+    cp_async_wait_group<kWideStages - 2>();   // slab `it` has landed (this thread's part)
+    __syncthreads();                          // ... everybody's; slab it-1 fully consumed
+    const double* As = gemm_smem + stage * S::kStageDoubles;
+    const double* Bs = As + BM * WLDA;
+#pragma unroll
+    for (int kk = 0; kk < WBK; kk += 4) {
+      double a[2], b[NT];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) a[i] = As[(wm * 16 + i * 8 + g) * WLDA + kk + t];
+#pragma unroll
+      for (int j = 0; j < NT; ++j) b[j] = Bs[(kk + t) * S::kLdb + wn * (8 * NT) + j * 8 + g];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) dmma_884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+      if (kk == 0) {
+        // refill the buffer consumed in the previous iteration while this warp's first
+        // DMMAs are queued in the pipe
+        const uint32_t nxt = it + kWideStages - 1;
+        int nstage = stage + kWideStages - 1;
+        if (nstage >= kWideStages) nstage -= kWideStages;
+        if (nxt < nslab) issue(nxt * WBK, nstage);
+        cp_async_commit();
+      }
+    }
+    if (++stage == kWideStages) stage = 0;
+  }
+  cp_async_wait_group<0>();
+
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const uint32_t row = m0 + wm * 16 + i * 8 + g;
+    if (row >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const uint32_t col = n0 + wn * (8 * NT) + j * 8 + 2 * t;
+      if (col >= p.N) continue;
+      const bool pair = (col + 1 < p.N);
+      gemm_store(Cg + (size_t)row * p.ldc + col, acc[i][j][0], acc[i][j][1], p.alpha_re,
+                 p.alpha_im, p.complex_pairs, p.accumulate, pair);
+      if (p.C2)
+        gemm_store(p.C2 + (size_t)row * p.ldc2 + col, acc[i][j][0], acc[i][j][1], p.alpha2_re,
+                   p.alpha2_im, p.complex_pairs, p.accumulate2, pair);
+    }
+  }
+}
+
+template <int NT>
+static cudaError_t launch_wide(const GemmArgs& p, int nbatch, cudaStream_t st) {
+  using S = WideShape<NT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(dht_gemm_wide_kernel<NT>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, S::kSmem);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  dim3 grid((p.N + S::kBN - 1) / S::kBN, (p.M + BM - 1) / BM, nbatch);
+  dht_gemm_wide_kernel<NT><<<grid, kWideThreads, S::kSmem, st>>>(p);
+  return cudaGetLastError();
+}
+
+// tile width (in units of 16 columns) minimising waves x width on 148 SMs
+static int pick_wide_nt(uint32_t M, uint32_t N, int nbatch) {
+  int best = 0;
+  double best_cost = 0;
+  for (int nt = 4; nt <= 8; ++nt) {
+    const uint64_t tiles = (uint64_t)((N + 16 * nt - 1) / (16 * nt)) * ((M + BM - 1) / BM) * nbatch;
+    const uint64_t waves = (tiles + kSMs - 1) / kSMs;
+    const double cost = (double)waves * nt;
+    if (best == 0 || cost <= best_cost) { best = nt; best_cost = cost; }
+  }
+  return best;
+}
+
 }  // namespace chb
 
 using namespace chb;
@@ -231,6 +420,18 @@ static int dht_launch(const double* A, uint32_t lda, const double* const* Bv, in
   bool vec = (p.lda % 2 == 0) && (p.ldb % 2 == 0) && (p.N % 2 == 0) &&
              (reinterpret_cast<uintptr_t>(A) % 16 == 0) && (p.lda > p.K || p.K % 2 == 0);
   for (int k = 0; k < nbatch && vec; ++k) vec = reinterpret_cast<uintptr_t>(Bv[k]) % 16 == 0;
+  const bool wide = vec && (p.ldc % 2 == 0) && (!C2 || p.ldc2 % 2 == 0) && !getenv("CHB_DHT_NARROW");
+  if (wide) {
+    cudaError_t e;
+    switch (pick_wide_nt(M, p.N, nbatch)) {
+      case 4: e = launch_wide<4>(p, nbatch, (cudaStream_t)stream); break;
+      case 5: e = launch_wide<5>(p, nbatch, (cudaStream_t)stream); break;
+      case 6: e = launch_wide<6>(p, nbatch, (cudaStream_t)stream); break;
+      case 7: e = launch_wide<7>(p, nbatch, (cudaStream_t)stream); break;
+      default: e = launch_wide<8>(p, nbatch, (cudaStream_t)stream); break;
+    }
+    return e == cudaSuccess ? CHB_OK : (int)e;
+  }
   if (vec)
     dht_gemm_kernel<true><<<grid, kGemmThreads, kGemmSmem, (cudaStream_t)stream>>>(p);
   else
