@@ -18,14 +18,26 @@
 //   * one FP64 RED per node value and CELL (not per particle) to the L2.
 // The four colour passes, their launches and the memsets between them are gone;
 // sums agree with the reference up to FP64 summation order.
+#include <cstdlib>
 #include "common.cuh"
 #include "../../include/chimera_b200.h"
 
 namespace chb {
 
-constexpr int kDepCells = 128;   // threads per CTA == cells per CTA
-constexpr int kDepBatch = 512;   // particles staged per batch
-constexpr int kDepPad = kDepBatch + kDepBatch / 16;
+// Two CTA geometries (template parameter CELLS):
+//   128 cells, batches of 512 particles, double buffered (the staging of batch b+1
+//        overlaps the accumulation of batch b; per batch only the warps owning its ~32
+//        cells accumulate, the others wait at the barrier);
+//    32 cells, ONE batch of up to 640 particles, single buffer: no CTA-wide pipeline at
+//        all -- every warp of the CTA accumulates at the same time, and the overlap of
+//        loads and arithmetic comes from the many small CTAs resident on an SM.
+template <int CELLS>
+struct DepGeom {
+  static constexpr int kCells = CELLS;
+  static constexpr bool kDouble = CELLS >= 128;
+  static constexpr int kBatch = kDouble ? 512 : CELLS * 20;
+  static constexpr int kPad = kBatch + kBatch / 16;
+};
 
 __device__ __forceinline__ int pidx(int j) { return j + (j >> 4); }
 
@@ -122,15 +134,25 @@ __device__ __noinline__ void deposit_derived(const Args& a, const GridVals& g,
 // of a cell are accumulated by three threads (each in a different warp, so the
 // component index is warp-uniform), which keeps the accumulators at 4*(1+2M) doubles
 // per thread and the occupancy high.
-template <bool VEC>
-struct DepShape { static constexpr int kThreads = kDepCells * (VEC ? 3 : 1); };
+// Threads per cell: the three current components (VEC), or -- small geometry, scalar --
+// the 2M+1 real mode values (m = 0, Re m = 1, Im m = 1, ...) of the charge density; each
+// thread then keeps only the four node accumulators of its value.
+template <int M, bool VEC, int CELLS>
+struct DepShape {
+  static constexpr bool kSplit = !VEC && CELLS < 128 && M > 0;
+  static constexpr int kPerCell = VEC ? 3 : (kSplit ? 2 * M + 1 : 1);
+  static constexpr int kThreads = CELLS * kPerCell;
+  // resident CTAs the launch bounds ask for (registers per thread follow from it)
+  static constexpr int kCtas = CELLS >= 128 ? (VEC ? 3 : 6) : (VEC ? 5 : (M > 1 ? 5 : 8));
+};
 
-template <int M, bool VEC>
+template <int M, bool VEC, int CELLS>
 struct DepSmem {
   // staged doubles per particle: raw attributes land here asynchronously and are
   // converted in place to (ax, ar, wp, [px, py, pz], [e0, e1])
   static constexpr int kSlots = VEC ? 8 : 5;
-  static constexpr int kBytes = 2 * kSlots * kDepPad * (int)sizeof(double);  // double buffered
+  static constexpr int kBytes = (DepGeom<CELLS>::kDouble ? 2 : 1) * kSlots * DepGeom<CELLS>::kPad *
+                                (int)sizeof(double);
 };
 
 // PUSH >= 1 (J only): the traversal order (sort_indx / cell_offset) is the one of the
@@ -144,14 +166,19 @@ struct DepSmem {
 // registers -- x2 = (x0 + d) + d with the same rounded increment d the two push_xyz
 // launches compute -- and x2's cell index and the cell histogram are produced here as
 // well: the pass also replaces the second push_coords and index_and_sum_in_cell.
-template <int M, bool VEC, int PUSH = 0>
-__global__ void __launch_bounds__(DepShape<VEC>::kThreads, VEC ? 3 : 6)
+template <int M, bool VEC, int PUSH = 0, int CELLS = 128>
+__global__ void __launch_bounds__(DepShape<M, VEC, CELLS>::kThreads, DepShape<M, VEC, CELLS>::kCtas)
 depose_kernel(const __grid_constant__ DepArgs<M, VEC> a) {
   static_assert(!PUSH || VEC, "the fused push exists for the current deposit only");
   constexpr int NC = VEC ? 3 : 1;
-  constexpr int NT = DepShape<VEC>::kThreads;
+  constexpr int NT = DepShape<M, VEC, CELLS>::kThreads;
+  constexpr bool SPLIT = DepShape<M, VEC, CELLS>::kSplit;
   constexpr int MM = M > 0 ? M : 1;
-  constexpr int NS = DepSmem<M, VEC>::kSlots;
+  constexpr int NS = DepSmem<M, VEC, CELLS>::kSlots;
+  constexpr int kDepCells = CELLS;
+  constexpr int kDepBatch = DepGeom<CELLS>::kBatch;
+  constexpr int kDepPad = DepGeom<CELLS>::kPad;
+  constexpr bool DB = DepGeom<CELLS>::kDouble;
   constexpr int KP = (kDepBatch + NT - 1) / NT;     // particles loaded per thread and batch
   // slot layout (VEC):   raw x y z px py pz w g_inv -> ax ar wp px py pz e0 e1
   // slot layout (!VEC):  raw x y z w  -          -> ax ar wp e0 e1
@@ -276,15 +303,20 @@ depose_kernel(const __grid_constant__ DepArgs<M, VEC> a) {
 
   load_sidx(P0);
   issue(P0, 0);
-  if (P0 + kDepBatch < P1) load_sidx(P0 + kDepBatch);
+  if (DB && P0 + kDepBatch < P1) load_sidx(P0 + kDepBatch);
 
   int buf = 0;
-  for (uint32_t b0 = P0; b0 < P1; b0 += kDepBatch, buf ^= 1) {
+  for (uint32_t b0 = P0; b0 < P1; b0 += kDepBatch, buf ^= (DB ? 1 : 0)) {
     const uint32_t b1 = min(b0 + (uint32_t)kDepBatch, P1);
+    if (!DB && b0 != P0) {        // crowded cells: further batches, one after the other
+      __syncthreads();            // the single buffer has been consumed
+      load_sidx(b0);
+      issue(b0, 0);
+    }
     cp_async_wait_all();          // this thread's copies of batch b0 have landed
     convert(b0, buf);
     __syncthreads();              // batch b0 ready for everyone; batch b0-1 fully consumed
-    if (b1 < P1) {                // overlap: stage the next batch while accumulating this one
+    if (DB && b1 < P1) {          // overlap: stage the next batch while accumulating this one
       issue(b1, buf ^ 1);
       if (b1 + kDepBatch < P1) load_sidx(b1 + kDepBatch);
     }
@@ -322,7 +354,7 @@ depose_kernel(const __grid_constant__ DepArgs<M, VEC> a) {
         for (int n = 0; n < 4; ++n) pj[n] = __dmul_rn(pj[n], jk);
       }
       double er[MM], ei[MM];
-      if (M > 0) {
+      if (M > 0 && !(SPLIT && comp == 0)) {
         er[0] = slot(buf, SL_E0, p);
         ei[0] = slot(buf, SL_E1, p);
 #pragma unroll
@@ -330,6 +362,23 @@ depose_kernel(const __grid_constant__ DepArgs<M, VEC> a) {
           er[m] = er[m - 1] * er[0] - ei[m - 1] * ei[0];
           ei[m] = er[m - 1] * ei[0] + ei[m - 1] * er[0];
         }
+      }
+      if (SPLIT) {
+        // this thread's value: comp = 0 -> m = 0; 2m-1 -> Re(mode m); 2m -> Im(mode m)
+        if (comp == 0) {
+#pragma unroll
+          for (int n = 0; n < 4; ++n) acc0[n] = __dadd_rn(acc0[n], pj[n]);
+        } else {
+          double f = 0.0;
+#pragma unroll
+          for (int m = 0; m < MM; ++m) {
+            if (comp == 2 * m + 1) f = er[m];
+            if (comp == 2 * m + 2) f = ei[m];
+          }
+#pragma unroll
+          for (int n = 0; n < 4; ++n) acc0[n] = fma(pj[n], f, acc0[n]);
+        }
+        continue;
       }
 #pragma unroll
       for (int n = 0; n < 4; ++n) {
@@ -346,6 +395,21 @@ depose_kernel(const __grid_constant__ DepArgs<M, VEC> a) {
   }
 
   // ---------------- flush: one RED per node value per cell
+  if (SPLIT) {
+    if (E > S) {
+      const int m = (comp + 1) >> 1;                 // mode of this thread's value
+      double* base = a.out[0];
+#pragma unroll
+      for (int k = 1; k <= MM; ++k)
+        if (m == k) base = a.out[k];
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+        const size_t node = (size_t)(ix + (n & 1)) + (size_t)(ir + (n >> 1)) * (size_t)g.Nx;
+        red_add_f64(comp == 0 ? base + node : base + 2 * node + ((comp & 1) ? 0 : 1), acc0[n]);
+      }
+    }
+    return;
+  }
   if (E > S) {
 #pragma unroll
     for (int n = 0; n < 4; ++n) {
@@ -405,15 +469,27 @@ depose_push_tail_kernel(const __grid_constant__ DepArgs<M, true> a) {
   }
 }
 
-template <int M, bool VEC, int PUSH = 0>
-static int launch_depose(DepArgs<M, VEC>& a, cudaStream_t st) {
-  uint32_t grid = (a.ncells + kDepCells - 1) / kDepCells;
-  constexpr int smem = DepSmem<M, VEC>::kBytes;
-  cudaError_t e = cudaFuncSetAttribute(depose_kernel<M, VEC, PUSH>,
+template <int M, bool VEC, int PUSH, int CELLS>
+static int launch_depose_geom(DepArgs<M, VEC>& a, cudaStream_t st) {
+  uint32_t grid = (a.ncells + CELLS - 1) / CELLS;
+  constexpr int smem = DepSmem<M, VEC, CELLS>::kBytes;
+  cudaError_t e = cudaFuncSetAttribute(depose_kernel<M, VEC, PUSH, CELLS>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return (int)e;
-  depose_kernel<M, VEC, PUSH><<<grid, DepShape<VEC>::kThreads, smem, st>>>(a);
+  depose_kernel<M, VEC, PUSH, CELLS><<<grid, DepShape<M, VEC, CELLS>::kThreads, smem, st>>>(a);
   CHB_RETURN_LAST_ERROR();
+}
+
+template <int M, bool VEC, int PUSH = 0>
+static int launch_depose(DepArgs<M, VEC>& a, cudaStream_t st) {
+  // measured on B200 (cfg3): the small geometry wins for the current (1.53 -> 1.11 ms,
+  // 41 % of the stall samples of the 128-cell kernel were warps waiting at the batch
+  // barrier), the large one for the charge (0.40 vs 0.43 ms).  CHB_DEP_CELLS=32|128
+  // forces one of them (profiling).
+  static const int forced = getenv("CHB_DEP_CELLS") ? atoi(getenv("CHB_DEP_CELLS")) : 0;
+  const int geom = forced ? forced : (VEC ? 32 : 128);
+  if (geom == 32) return launch_depose_geom<M, VEC, PUSH, 32>(a, st);
+  return launch_depose_geom<M, VEC, PUSH, 128>(a, st);
 }
 
 // ------------------------------------------------------------------ grid fix-ups
