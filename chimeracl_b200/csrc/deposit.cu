@@ -35,7 +35,7 @@ template <int CELLS>
 struct DepGeom {
   static constexpr int kCells = CELLS;
   static constexpr bool kDouble = CELLS >= 128;
-  static constexpr int kBatch = kDouble ? 512 : CELLS * 20;
+  static constexpr int kBatch = kDouble ? 512 : CELLS * 17;
   static constexpr int kPad = kBatch + kBatch / 16;
 };
 
@@ -143,7 +143,7 @@ struct DepShape {
   static constexpr int kPerCell = VEC ? 3 : (kSplit ? 2 * M + 1 : 1);
   static constexpr int kThreads = CELLS * kPerCell;
   // resident CTAs the launch bounds ask for (registers per thread follow from it)
-  static constexpr int kCtas = CELLS >= 128 ? (VEC ? 3 : 6) : (VEC ? 5 : (M > 1 ? 5 : 8));
+  static constexpr int kCtas = CELLS >= 128 ? (VEC ? 3 : 6) : (VEC ? 6 : (M > 1 ? 5 : 8));
 };
 
 template <int M, bool VEC, int CELLS>
