@@ -373,9 +373,36 @@ static int pick_wide_nt(uint32_t M, uint32_t N, int nbatch) {
   return best;
 }
 
+// Register-only DMMA loop: the FP64 tensor pipe's issue ceiling on this device (the
+// roofline denominator bench.py reports for the contraction; MEASURED_PEAKS.json has no
+// FP64 entry).  16 warps per SM, 8 independent accumulators per warp.
+__global__ void __launch_bounds__(512) dmma_peak_kernel(double* out, int iters) {
+  double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+  double c[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) c[i] = i;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; i += 2) dmma_884(c[i], c[i + 1], a, b);
+  }
+  double sum = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) sum += c[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = sum;
+}
+
 }  // namespace chb
 
 using namespace chb;
+
+extern "C" int chb_dmma_peak(double* scratch, size_t scratch_doubles, int iters,
+                             double* flops_out, void* stream) {
+  if (scratch_doubles < (size_t)kSMs * 512 || iters <= 0 || !flops_out) return CHB_ERR_ARG;
+  dmma_peak_kernel<<<kSMs, 512, 0, (cudaStream_t)stream>>>(scratch, iters);
+  // 16 warps x 8 DMMA.8x8x4 (512 flop each) per iteration and SM
+  *flops_out = (double)kSMs * 16.0 * 8.0 * 512.0 * (double)iters;
+  CHB_RETURN_LAST_ERROR();
+}
 
 static int dht_launch(const double* A, uint32_t lda, const double* const* Bv, int nbatch,
                       uint32_t ldb, double* const* Cv, uint32_t ldc, uint32_t M, uint32_t K,

@@ -226,6 +226,12 @@ int chb_psatd_advance(size_t n, const double* dt_inv_dev, const double* c1, cons
 
 /* ---------------------------------------------------------------- spectral: DHT and FFT */
 
+/* Measurement aid (bench.py): launches a register-only FP64 DMMA loop on every SM;
+ * flops_out = floating-point operations it executes (time it with events on `stream`).
+ * scratch: >= 148*512 doubles of device memory.  No reference counterpart. */
+int chb_dmma_peak(double* scratch, size_t scratch_doubles, int iters, double* flops_out,
+                  void* stream);
+
 /* C (op)= alpha * A . B with A real (M x K, leading dimension lda), B and C real
  * (is_complex=0) or complex (is_complex=1) with N columns and leading dimensions
  * ldb/ldc given in ELEMENTS of their type; op is '=' or '+=' (accumulate).  A complex
