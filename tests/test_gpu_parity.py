@@ -563,3 +563,52 @@ def test_one_pass_particle_side_equals_reference_sequence(comm, M):
     for k in S1.DataDev:
         if k.startswith(("Jx_m", "Jy_m", "Jz_m")):
             assert rel_err(S2.DataDev[k].get(), S1.DataDev[k].get()) < 1e-12, k
+
+
+def test_diagnostics_records(comm, tmp_path, monkeypatch):
+    """Diagnostics.make_record (reference diagnostics.py:57-141) hooked into
+    PIC_loop.step(): record layout /data/{info,fields,species}, modes stacked as
+    [m0, Re m1, Im m1], particle selection windows and the w2pC weight scaling."""
+    import importlib.util
+    import os
+    from chimeracl_b200.diagnostics import Diagnostics
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                        "examples", "lpa_script_small.py")
+    spec = importlib.util.spec_from_file_location("lpa_small_diag", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    _, solver, eons, ions, frame, loop = mod.build(Nx=200, Nr=40, M=1, comm=comm)
+    monkeypatch.chdir(tmp_path)
+    diag_in = {"Interval": 2, "ScalarFields": ["rho", "Ez"], "VectorFields": ["B"], "w2pC": 2.5,
+               "Species": {"Components": ["x", "w", "px"], "Selections": [["px", -0.5, None]]}}
+    diag = Diagnostics(diag_in, solver, species=[eons, ions][:1], frame=frame)
+    loop.diags = [diag]
+    for _ in range(3):
+        loop.step()
+    files = sorted(os.listdir(tmp_path / "diags"))
+    assert files == ["000000000.npz", "000000002.npz"]      # it = 0 and it = 2
+    rec = np.load(tmp_path / "diags" / files[1])
+    assert int(rec["/data/info/iteration"]) == 2
+    assert float(rec["/data/info/FrameVelocity"]) == frame.Args["Velocity"]
+    assert rec["/data/info/Xgrid"].shape == (solver.Args["Nx"],)
+    Nr, Nx = solver.Args["Nr"], solver.Args["Nx"]
+    for name in ("rho", "Ez", "Bx", "By", "Bz"):
+        fld = rec["/data/fields/" + name]
+        assert fld.shape == (3, Nr, Nx) and fld.dtype == np.float32, name
+        assert np.isfinite(fld).all(), name
+    assert np.abs(rec["/data/fields/Ez"]).max() > 0.1        # the laser is in the box
+    px = rec["/data/species/species_0/px"]
+    assert px.dtype == np.float64 and (px > -0.5).all()
+    assert rec["/data/species/species_0/x"].shape == px.shape
+    # selection and weight scaling against the device data of the same iteration:
+    # a record written now (no step in between) must reproduce the current arrays
+    diag.Args["Interval"] = 1
+    diag.make_record(loop.it)
+    now = np.load(tmp_path / "diags" / ("%09d.npz" % loop.it))
+    keep = eons.DataDev["px"].get() > -0.5
+    assert np.array_equal(now["/data/species/species_0/x"], eons.DataDev["x"].get()[keep])
+    assert np.allclose(now["/data/species/species_0/w"], 2.5 * eons.DataDev["w"].get()[keep],
+                       rtol=1e-15)
+    Ez = solver.DataDev["Ez_m1"].get()
+    assert np.array_equal(now["/data/fields/Ez"][1], Ez.real.astype(np.float32))
+    assert np.array_equal(now["/data/fields/Ez"][2], Ez.imag.astype(np.float32))
