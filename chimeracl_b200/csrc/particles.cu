@@ -213,16 +213,37 @@ sort_scatter_kernel(const uint32_t* __restrict__ indx_in_cell,
                     uint32_t n) {
   const int lane = threadIdx.x & 31;
   const uint32_t n_round = ((n + 31u) / 32u) * 32u;
-  const uint32_t stride = gridDim.x * kBlock;
-  for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i - lane < n_round; i += stride) {
-    bool valid = i < n;
-    uint32_t cell = valid ? indx_in_cell[i] : 0xffffffffu;
-    int head, rank, len;
-    warp_runs(cell, valid, lane, head, rank, len);
-    uint32_t basev = 0;
-    if (valid && rank == 0) basev = atomicAdd(&cursor[cell], (uint32_t)len);
-    basev = __shfl_sync(0xffffffffu, basev, head);
-    if (valid) sort_indx[basev + rank] = i;
+  const uint32_t stride = gridDim.x * kBlock * kIlp;
+  // kIlp independent particles per thread: the slot-claiming atomics of all of them are
+  // in flight before the first result is needed
+  for (uint32_t base = blockIdx.x * kBlock * kIlp + threadIdx.x; base - lane < n_round;
+       base += stride) {
+    uint32_t cell[kIlp], basev[kIlp];
+    int head[kIlp], rank[kIlp];
+#pragma unroll
+    for (int k = 0; k < kIlp; ++k) {
+      const uint32_t i = base + k * kBlock;
+      cell[k] = i < n ? indx_in_cell[i] : 0xffffffffu;
+    }
+#pragma unroll
+    for (int k = 0; k < kIlp; ++k) {
+      const uint32_t i = base + k * kBlock;
+      basev[k] = 0;
+      head[k] = rank[k] = 0;
+      if (i - lane < n_round) {            // warp-uniform
+        int len;
+        warp_runs(cell[k], i < n, lane, head[k], rank[k], len);
+        if (i < n && rank[k] == 0) basev[k] = atomicAdd(&cursor[cell[k]], (uint32_t)len);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kIlp; ++k) {
+      const uint32_t i = base + k * kBlock;
+      if (i - lane < n_round) {
+        const uint32_t b = __shfl_sync(0xffffffffu, basev[k], head[k]);
+        if (i < n) sort_indx[b + rank[k]] = i;
+      }
+    }
   }
 }
 
@@ -551,7 +572,7 @@ int chb_sort_scatter_stable(const uint32_t* indx_in_cell, const uint32_t* cell_o
   uint32_t* tmp = giant_list + CHB_GIANT_CAP;
   cudaError_t e = cudaMemsetAsync(giant_count, 0, sizeof(uint32_t), st);
   if (e != cudaSuccess) return (int)e;
-  sort_scatter_kernel<<<stream_grid(np, kBlock, 16), kBlock, 0, st>>>(indx_in_cell, cursor,
+  sort_scatter_kernel<<<stream_grid(np, kBlock * kIlp, 8), kBlock, 0, st>>>(indx_in_cell, cursor,
                                                                       sort_indx, np);
   int fgrid = stream_grid(nbins, kFixBlock, 8);
   sort_fixup_kernel<<<fgrid, kFixBlock, 0, st>>>(cell_offset, nbins, sort_indx, giant_count,
