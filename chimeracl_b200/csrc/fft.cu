@@ -103,9 +103,13 @@ __device__ __forceinline__ void store_out(const FftArgs& a, double* row, int ix,
 // of the shared buffer; LAST: the outputs go straight to global memory (with the fused
 // epilogue).  Both accesses are coalesced: the first pass reads j + r*N/R, the last
 // pass (NS = N/R) writes k + r*NS, consecutive in the thread index.
-template <int LOGN, int LR, int NS, bool FIRST, bool LAST>
+// REG (chained transforms, fft_damp_kernel): the first pass takes its inputs from / the
+// last pass leaves its outputs in the register file instead, io[m] <-> element
+// tid + m*N/8 -- the first pass reads and the last pass writes exactly that element set.
+template <int LOGN, int LR, int NS, bool FIRST, bool LAST, bool REG = false>
 __device__ __forceinline__ void stockham_pass(double2* s, const double2* __restrict__ tw, int tid,
-                                              const FftArgs& a, const double* rin, double* rout) {
+                                              const FftArgs& a, const double* rin, double* rout,
+                                              double2* io = nullptr) {
   constexpr int N = 1 << LOGN, T = N >> 3, R = 1 << LR, NB = 8 >> LR;
   double2 v[8];
 #pragma unroll
@@ -113,7 +117,8 @@ __device__ __forceinline__ void stockham_pass(double2* s, const double2* __restr
     const int j = tid + q * T;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      if (FIRST) v[q * R + r] = load_in(a, rin, j + r * (N / R));
+      if (FIRST && REG) v[q * R + r] = io[q + r * (8 / R)];
+      else if (FIRST) v[q * R + r] = load_in(a, rin, j + r * (N / R));
       else v[q * R + r] = s[pad(j + r * (N / R))];
     }
   }
@@ -138,30 +143,33 @@ __device__ __forceinline__ void stockham_pass(double2* s, const double2* __restr
     const int j0 = ((j - k) << LR) + k;   // (j / NS) * NS * R + k
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      if (LAST) store_out(a, rout, j0 + r * NS, b[r]);
+      if (LAST && REG) io[q + r * (8 / R)] = b[r];
+      else if (LAST) store_out(a, rout, j0 + r * NS, b[r]);
       else s[pad(j0 + r * NS)] = b[r];
     }
   }
   if (!LAST) __syncthreads();
 }
 
-// GLOBAL_IO: first pass loads from / last pass stores to global memory
-template <int LOGN, int DONE, int NS, bool GLOBAL_IO>
+// GLOBAL_IO: first pass loads from / last pass stores to global memory (REG: registers)
+template <int LOGN, int DONE, int NS, bool GLOBAL_IO, bool REG = false>
 struct Passes {
   static __device__ __forceinline__ void run(double2* s, const double2* __restrict__ tw, int tid,
-                                             const FftArgs& a, const double* rin, double* rout) {
+                                             const FftArgs& a, const double* rin, double* rout,
+                                             double2* io = nullptr) {
     constexpr int REM = LOGN - DONE;
     constexpr int LR = REM >= 3 ? 3 : REM;
     constexpr bool FIRST = GLOBAL_IO && DONE == 0;
     constexpr bool LAST = GLOBAL_IO && (DONE + LR == LOGN);
-    stockham_pass<LOGN, LR, NS, FIRST, LAST>(s, tw, tid, a, rin, rout);
-    Passes<LOGN, DONE + LR, (NS << LR), GLOBAL_IO>::run(s, tw, tid, a, rin, rout);
+    stockham_pass<LOGN, LR, NS, FIRST, LAST, REG>(s, tw, tid, a, rin, rout, io);
+    Passes<LOGN, DONE + LR, (NS << LR), GLOBAL_IO, REG>::run(s, tw, tid, a, rin, rout, io);
   }
 };
-template <int LOGN, int NS, bool GLOBAL_IO>
-struct Passes<LOGN, LOGN, NS, GLOBAL_IO> {
+template <int LOGN, int NS, bool GLOBAL_IO, bool REG>
+struct Passes<LOGN, LOGN, NS, GLOBAL_IO, REG> {
   static __device__ __forceinline__ void run(double2*, const double2* __restrict__, int,
-                                             const FftArgs&, const double*, double*) {}
+                                             const FftArgs&, const double*, double*,
+                                             double2* = nullptr) {}
 };
 
 // In-place forward FFT of the padded buffer s (natural order in, natural order
@@ -185,6 +193,73 @@ fft_pow2_kernel(FftArgs a) {
   // an extra round trip through shared memory, and an in-place call is safe because
   // every input of the row is in registers/smem before the last pass writes
   Passes<LOGN, 0, 1, true>::run(s, a.tw, tid, a, rin, rout);
+}
+
+// damp_fields of the reference (solver.py:32-35) on one spectral row, in place:
+//   half backward transform (x phase, inverse FFT, real part for m = 0)
+//   -> profile_edges (solver_ms_pic.cl:5-55: Nf edge columns on each side times prof)
+//   -> half forward transform (FFT, x phase)
+// The row stays on chip between the two transforms (the last pass of the first one
+// leaves in registers exactly the elements the first pass of the second one needs), so
+// it is read and written once instead of three times; every element goes through the
+// same operations as in the three separate calls (bit-identical results).
+struct DampArgs {
+  double* row[CHB_MAX_FIELDS];     // spectral arrays (complex rows), transformed in place
+  int real_x[CHB_MAX_FIELDS];      // m = 0: the x-space half transform keeps the real part
+  size_t stride;                   // complex elements between rows
+  const double2* tw;
+  const double2* phase_bwd;        // exp(+i kx Xmin) applied before the inverse FFT
+  const double2* phase_fwd;        // exp(-i kx Xmin) applied after the forward FFT
+  const double* prof;
+  int N, Nf;
+};
+
+template <int LOGN>
+__global__ void __launch_bounds__((1 << LOGN) / 8 < 32 ? 32 : (1 << LOGN) / 8)
+fft_damp_kernel(DampArgs d) {
+  extern __shared__ double2 s[];
+  constexpr int N = 1 << LOGN, T = N >> 3;
+  const int tid = threadIdx.x;
+  double2* row = reinterpret_cast<double2*>(d.row[blockIdx.y]) + (size_t)blockIdx.x * d.stride;
+  const bool real_x = d.real_x[blockIdx.y] != 0;
+  FftArgs dummy;
+  double2 io[8];
+  // inverse transform as conj(FFT(conj(.))) / N, phase on the input
+#pragma unroll
+  for (int m = 0; m < 8; ++m) {
+    const int ix = tid + m * T;
+    io[m] = cconj(cmulf(row[ix], __ldg(d.phase_bwd + ix)));
+  }
+  Passes<LOGN, 0, 1, true, true>::run(s, d.tw, tid, dummy, nullptr, nullptr, io);
+  const double scale = 1.0 / (double)N;
+#pragma unroll
+  for (int m = 0; m < 8; ++m) {
+    const int ix = tid + m * T;
+    double2 v = cconj(io[m]);
+    v.x *= scale; v.y *= scale;
+    if (real_x) v.y = 0.0;
+    if (ix < d.Nf) { const double f = __ldg(d.prof + ix); v.x *= f; if (!real_x) v.y *= f; }
+    if (ix > N - d.Nf) { const double f = __ldg(d.prof + (N - ix)); v.x *= f; if (!real_x) v.y *= f; }
+    io[m] = v;
+  }
+  __syncthreads();   // the shared buffer of the first transform is free again
+  Passes<LOGN, 0, 1, true, true>::run(s, d.tw, tid, dummy, nullptr, nullptr, io);
+#pragma unroll
+  for (int m = 0; m < 8; ++m) {
+    const int ix = tid + m * T;
+    row[ix] = cmulf(io[m], __ldg(d.phase_fwd + ix));
+  }
+}
+
+template <int LOGN>
+static int launch_damp(const DampArgs& d, uint32_t rows, int nbatch, cudaStream_t st) {
+  constexpr int L = 1 << LOGN;
+  const size_t smem = (size_t)padded_len(L) * sizeof(double2);
+  cudaError_t e = cudaFuncSetAttribute(fft_damp_kernel<LOGN>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  fft_damp_kernel<LOGN><<<dim3(rows, nbatch), L / 8, smem, st>>>(d);
+  CHB_RETURN_LAST_ERROR();
 }
 
 // Rows longer than one CTA's shared memory (N = 16384: 256 KiB): one radix-2
@@ -320,6 +395,39 @@ int chb_fft_x_batched(const double* const* in_host, double* const* out_host, int
     case 11: return launch_fft<11>(a, pow2, rows, nbatch, st);
     case 12: return launch_fft<12>(a, pow2, rows, nbatch, st);
     case 13: return launch_fft<13>(a, pow2, rows, nbatch, st);
+    default: return CHB_ERR_ARG;
+  }
+}
+
+int chb_fft_damp_x_batched(double* const* spec_host, const int* real_x_host, int nbatch,
+                           uint32_t rows, uint32_t Nx, size_t stride, const double* phase_bwd,
+                           const double* phase_fwd, const double* prof, uint32_t Nf,
+                           const double* twiddles, void* stream) {
+  if (rows == 0 || nbatch == 0) return CHB_OK;
+  if (nbatch < 0 || nbatch > CHB_MAX_FIELDS) return CHB_ERR_ARG;
+  if (Nx < 256 || (Nx & (Nx - 1)) || Nx > 8192 || Nf > Nx || !phase_bwd || !phase_fwd || !prof)
+    return CHB_ERR_ARG;                    // one CTA per row, 32..1024 threads
+  DampArgs d;
+  for (int k = 0; k < CHB_MAX_FIELDS; ++k) {
+    d.row[k] = k < nbatch ? spec_host[k] : nullptr;
+    d.real_x[k] = k < nbatch ? real_x_host[k] : 0;
+  }
+  d.stride = stride;
+  d.tw = (const double2*)twiddles;
+  d.phase_bwd = (const double2*)phase_bwd;
+  d.phase_fwd = (const double2*)phase_fwd;
+  d.prof = prof;
+  d.N = (int)Nx; d.Nf = (int)Nf;
+  cudaStream_t st = (cudaStream_t)stream;
+  int logN = 0;
+  while ((1u << logN) < Nx) ++logN;
+  switch (logN) {
+    case 8: return launch_damp<8>(d, rows, nbatch, st);
+    case 9: return launch_damp<9>(d, rows, nbatch, st);
+    case 10: return launch_damp<10>(d, rows, nbatch, st);
+    case 11: return launch_damp<11>(d, rows, nbatch, st);
+    case 12: return launch_damp<12>(d, rows, nbatch, st);
+    case 13: return launch_damp<13>(d, rows, nbatch, st);
     default: return CHB_ERR_ARG;
   }
 }

@@ -41,6 +41,35 @@ class SolverMethodsCL(GenericMethodsCL):
                        D['MxSlv_cos(wdt)' + ms].ptr, D['MxSlv_sin(wdt)*w' + ms].ptr,
                        D['MxSlv_1/w**2' + ms].ptr, *groups)
 
+    def damp_fields_fused(self, flds):
+        """The three calls of damp_fields (reference solver.py:32-35) as one in-place,
+        on-chip pass per spectral row (chb_fft_damp_x_batched): same arithmetic per
+        element, but the x-space intermediate never goes to the E/G grid arrays (the
+        reference only uses them as scratch at this point).  Returns False when the
+        shape is not covered (Nx not a power of two in [256, 8192], no damping) and
+        the caller should run the three separate calls."""
+        Nx = int(self.Args['Nx'])
+        if 'DampProfile' not in self.DataDev or Nx < 256 or Nx > 8192 or Nx & (Nx - 1):
+            return False
+        if getattr(self, '_fft_L', None) != Nx:
+            return False
+        D = self.DataDev
+        phs_b, phs_f = self._phase(1), self._phase(0)
+        arrays, real_x = [], []
+        for fld in flds:
+            for comp in self.Args['vec_comps']:
+                for m in range(self.Args['M'] + 1):
+                    arrays.append(D[fld + comp + '_fb_m' + str(m)])
+                    real_x.append(1 if m == 0 else 0)
+        rows = int(self.Args['Nr']) - 1
+        for i in range(0, len(arrays), 16):
+            chunk = arrays[i:i + 16]
+            self._call('chb_fft_damp_x_batched', _lib.ptr_array([a.ptr for a in chunk]),
+                       _lib.int_array(real_x[i:i + 16]), len(chunk), rows, Nx,
+                       chunk[0].t.stride(0), phs_b.ptr, phs_f.ptr, D['DampProfile'].ptr,
+                       2 * int(self.Args['DampCells']), self._fft_tw.ptr)
+        return True
+
     def profile_edges(self, flds):
         arrays = []
         for fld in flds:

@@ -37,6 +37,8 @@ class Solver(Grid, Transformer, SolverMethodsCL):
         self.advance_fields(vecs=['E', 'G', 'J', 'dN0', 'dN1'])
 
     def damp_fields(self):
+        if self.damp_fields_fused(['E', 'G']):
+            return
         self.fb_transform(vects=['E', 'G'], dir=1, mode='half')
         self.profile_edges(['E', 'G'])
         self.fb_transform(vects=['E', 'G'], dir=0, mode='half')

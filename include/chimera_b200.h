@@ -271,6 +271,19 @@ int chb_dht2(const double* A, uint32_t lda, const double* B, uint32_t ldb, doubl
  * Replaces Reikna FFT `_fft`, methods/transformer_methods_cl.py:482-509, plus the
  * cast / phase / slice-copy passes around it (:295-311, :338-358). */
 int chb_fft_max_pow2(void);
+/* damp_fields (solver.py:32-35) on the spectral arrays, in place and on chip: half
+ * backward transform (x phase `phase_bwd`, inverse FFT, real part where real_x_host[k]),
+ * profile_edges (kernels/solver_ms_pic.cl:5-55; columns ix < Nf and ix > Nx-Nf times
+ * prof[ix] / prof[Nx-ix]), half forward transform (FFT, x phase `phase_fwd`).  Replaces
+ * the sequence transform_field(dir=1,'half') -> profile_edges -> transform_field(dir=0,
+ * 'half') (transformer_methods_cl.py:385-455, solver_methods_cl.py:64-83) with the same
+ * per-element arithmetic; the x-space intermediate is not written to the grid arrays.
+ * Nx: power of two in [256, 8192]; stride in complex elements. */
+int chb_fft_damp_x_batched(double* const* spec_host, const int* real_x_host, int nbatch,
+                           uint32_t rows, uint32_t Nx, size_t stride, const double* phase_bwd,
+                           const double* phase_fwd, const double* prof, uint32_t Nf,
+                           const double* twiddles, void* stream);
+
 /* The same transform applied to nbatch <= CHB_MAX_FIELDS arrays in one launch;
  * out_filter (rows x Nx real, may be NULL) multiplies the output: the spectral
  * smoothing of fields_smooth, transformer_methods_cl.py:79-85, folded into the

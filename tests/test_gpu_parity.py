@@ -612,3 +612,36 @@ def test_diagnostics_records(comm, tmp_path, monkeypatch):
     Ez = solver.DataDev["Ez_m1"].get()
     assert np.array_equal(now["/data/fields/Ez"][1], Ez.real.astype(np.float32))
     assert np.array_equal(now["/data/fields/Ez"][2], Ez.imag.astype(np.float32))
+
+
+@pytest.mark.parametrize("M,Nx", [(0, 256), (1, 512), (2, 1024)])
+def test_fused_damp_fields_equals_three_calls(comm, M, Nx):
+    """Solver.damp_fields through chb_fft_damp_x_batched (inverse FFT -> edge profile ->
+    FFT, in place and on chip) against the reference's three calls (solver.py:32-35):
+    every element sees the same operations, so the spectra must be bit-identical; a
+    non-zero Xmin exercises both x-phase tables."""
+    from chimeracl_b200.solver import Solver
+    cfg = {"Xmin": -3.7, "Xmax": 9.1, "Nx": Nx, "Rmin": 0.0, "Rmax": 5.0, "Nr": 33, "M": M,
+           "DampCells": 30}
+    S1, S2 = Solver(dict(cfg), comm), Solver(dict(cfg), comm)
+    rng = np.random.default_rng(5 + M)
+    for k in sorted(S1.DataDev):
+        if k[0] in "EG" and "_fb_m" in k:
+            a = rng.normal(size=S1.DataDev[k].shape) + 1j * rng.normal(size=S1.DataDev[k].shape)
+            S1.DataDev[k][:] = a
+            S2.DataDev[k][:] = a
+    assert S1.damp_fields_fused(["E", "G"]) is True
+    S2.fb_transform(vects=["E", "G"], dir=1, mode="half")
+    S2.profile_edges(["E", "G"])
+    S2.fb_transform(vects=["E", "G"], dir=0, mode="half")
+    checked = 0
+    for k in sorted(S1.DataDev):
+        if k[0] in "EG" and "_fb_m" in k:
+            a, b = S1.DataDev[k].get(), S2.DataDev[k].get()
+            assert np.array_equal(a, b), (k, np.abs(a - b).max())
+            checked += 1
+    assert checked == 6 * (M + 1)
+    # and the damping really acted: the x-space edge columns are attenuated
+    S2.fb_transform(vects=["E"], dir=1, mode="half")
+    ex = np.abs(S2.DataDev["Ex_m0"].get()[1:])
+    assert ex[:, 0].max() < 1e-6 * ex[:, Nx // 2].max()
