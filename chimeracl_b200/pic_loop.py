@@ -83,6 +83,11 @@ class PIC_loop:
         self.timer_record('depose')
 
         self._push_and_sort()
+        # x, y, z now hold their end-of-step values (the rest of the step only changes
+        # the momenta): a caller streaming results to the host can start copying them
+        hook = getattr(self, 'on_coordinates_final', None)
+        if hook is not None:
+            hook(self)
 
         for solver in self.solvers:
             self.timer_start()

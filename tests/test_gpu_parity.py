@@ -645,3 +645,32 @@ def test_fused_damp_fields_equals_three_calls(comm, M, Nx):
     S2.fb_transform(vects=["E"], dir=1, mode="half")
     ex = np.abs(S2.DataDev["Ex_m0"].get()[1:])
     assert ex[:, 0].max() < 1e-6 * ex[:, Nx // 2].max()
+
+
+@pytest.mark.parametrize("overlap", [False, True])
+def test_host_buffer_step(comm, overlap):
+    """host_api.step_from_host (the e2e path of bench.py): attributes uploaded from pinned
+    host memory, one PIC step, results downloaded -- with and without the early
+    coordinate download on the second stream; the host copies must equal the device
+    arrays, and both variants must give the same step."""
+    import torch
+    from chimeracl_b200 import host_api
+    from chimeracl_b200.solver import Solver
+    from chimeracl_b200.pic_loop import PIC_loop
+    cfg = {"Xmin": -1.0, "Xmax": 1.0, "Nx": 64, "Rmin": 0.0, "Rmax": 1.0, "Nr": 32, "M": 1,
+           "DampCells": 8}
+    S = Solver(dict(cfg), comm)
+    P, _ = _random_species(comm, 50000, (-0.9, 0.9), seed=21, spread=0.3)
+    P.sort_parts(S)
+    loop = PIC_loop(solvers=[S], species=[P])
+    loop.step()
+    host_in, host_out = host_api.make_host_buffers(P, S)
+    x_before = host_in["x"].numpy().copy()
+    h2d, d2h = host_api.step_from_host(loop, P, host_in, host_out, overlap=overlap)
+    torch.cuda.synchronize()
+    assert h2d == 8 * 8 * P.Args["Np"] and d2h == 7 * 8 * P.Args["Np"] + 8 * 64 * 32
+    for a in host_api.ATTRS_OUT:
+        assert np.array_equal(host_out[a].numpy(), P.DataDev[a].get()), a
+    assert np.array_equal(host_out["rho_m0"].numpy(), S.DataDev["rho_m0"].get())
+    assert not np.array_equal(host_out["x"].numpy(), x_before)      # the step moved them
+    assert loop.on_coordinates_final is None
