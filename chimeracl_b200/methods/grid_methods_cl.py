@@ -64,6 +64,7 @@ class GridMethodsCL(GenericMethodsCL):
                        P['cell_offset'].ptr, P[push_dt].ptr, int(parts.Args['Np']),
                        int(np.int8(charge)), *self._geom(), _lib.ptr_array(flds),
                        indx.ptr, hist.ptr, *parts.exception_workspace())
+            parts.exception_count_readback()
             parts.flag_sorted = False
             parts._index_prefilled = True
             return
@@ -76,6 +77,7 @@ class GridMethodsCL(GenericMethodsCL):
                        P['cell_offset'].ptr, P[push_dt].ptr, int(parts.Args['Np']),
                        int(np.int8(charge)), *self._geom(), _lib.ptr_array(flds),
                        *parts.exception_workspace())
+            parts.exception_count_readback()
             parts.flag_sorted = False
             return
         # factors = ['g_inv', 'w'] in the reference call (grid.py:49-51)

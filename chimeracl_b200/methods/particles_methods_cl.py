@@ -52,10 +52,46 @@ class ParticleMethodsCL(GenericMethodsCL):
                 and self.DataDev['sort_indx'].size == self.Args['Np'])
 
     def exception_workspace(self):
-        """(pointer, bytes) of the scratch chb_push_depose_vector / _push_index need."""
-        nbytes = int(self._lib.chb_push_depose_workspace_bytes(int(self.Args['Np'])))
+        """(pointer, bytes) of the scratch chb_push_depose_vector / _push_index need: the
+        queue of the particles that changed cell.  Sized for the worst case (one 64-byte
+        record per particle) up to 4 GiB; beyond that a quarter of the particles, with the
+        device-side counter read back asynchronously and checked before the next use
+        (an overflow means the previous step's current was incomplete: raise)."""
+        Np = int(self.Args['Np'])
+        full = int(self._lib.chb_push_depose_workspace_bytes(Np))
+        limit = getattr(self, '_exc_full_limit', 4 << 30)
+        nbytes = full if full <= limit else 16 + 64 * (Np // 4 + 4096)
+        self._check_exception_overflow()
         ws = self._buf('exc_ws', (nbytes + 7) // 8, np.double)
+        if nbytes < full:
+            cap = (nbytes - 16) // 64
+            if getattr(self, '_exc_host', None) is None:
+                self._exc_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+            self._exc_pending = (cap, ws)      # read back after the launch, see below
         return ws.ptr, nbytes
+
+    def exception_count_readback(self):
+        """Enqueue the asynchronous read-back of the cell-changer counter (only needed
+        when the queue is smaller than the worst case)."""
+        pend = self.__dict__.pop('_exc_pending', None)
+        if pend is None:
+            return
+        cap, ws = pend
+        self._exc_host.copy_(ws.t[:1].view(torch.int32)[:1], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._exc_check = (cap, ev)
+
+    def _check_exception_overflow(self):
+        chk = self.__dict__.pop('_exc_check', None)
+        if chk is None:
+            return
+        cap, ev = chk
+        ev.synchronize()
+        n = int(self._exc_host.item()) & 0xffffffff
+        if n > cap:
+            raise RuntimeError("chimera_b200: %d particles changed cell in one step but the "
+                               "queue holds %d; the deposited current was incomplete" % (n, cap))
 
     def add_new_particles(self, source=None):
         self._order_np = -1

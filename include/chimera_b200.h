@@ -118,8 +118,11 @@ int chb_depose_vector(int M, const uint32_t* sort_indx, const double* x, const d
  * particles still in the cell that order assumes take the cell-ordered fast path, the
  * others (and the previous trash bin) are deposited one by one.  Same sums as
  * chb_push_xyz -> sort -> chb_depose_vector up to summation order; np = all particles;
- * workspace (8-byte aligned): chb_push_depose_workspace_bytes(np) bytes (queue of the
- * cell changers, sized for the worst case; CHB_ERR_WORKSPACE if smaller). */
+ * workspace (8-byte aligned): a u32 counter (16 bytes reserved) followed by the queue of
+ * the cell changers, 64 bytes each; chb_push_depose_workspace_bytes(np) is the size that
+ * can never overflow (one record per particle).  With a smaller workspace the caller must
+ * read the counter back: a value above (workspace_bytes - 16) / 64 means records were
+ * dropped and the deposited current is incomplete. */
 size_t chb_push_depose_workspace_bytes(uint32_t np);
 int chb_push_depose_vector(int M, const uint32_t* sort_indx, double* x, double* y, double* z,
                            const double* px, const double* py, const double* pz,

@@ -674,3 +674,36 @@ def test_host_buffer_step(comm, overlap):
     assert np.array_equal(host_out["rho_m0"].numpy(), S.DataDev["rho_m0"].get())
     assert not np.array_equal(host_out["x"].numpy(), x_before)      # the step moved them
     assert loop.on_coordinates_final is None
+
+
+def test_cell_changer_queue_overflow_is_detected(comm):
+    """With more than 4 GiB of worst-case queue the fused pass gets a quarter-size queue
+    and the device counter is checked before the next use: an overflow (incomplete J)
+    must raise instead of passing silently; a sufficient queue must not."""
+    from chimeracl_b200.solver import Solver
+    from chimeracl_b200.particles import Particles
+    cfg = {"Xmin": -1.0, "Xmax": 1.0, "Nx": 48, "Rmin": 0.0, "Rmax": 1.0, "Nr": 24, "M": 1}
+    rng = np.random.default_rng(91)
+    n = 120000
+
+    def make(pscale):
+        S = Solver(dict(cfg), comm)
+        arrays = {"x": rng.uniform(-0.9, 0.9, n), "y": rng.normal(0, 0.3, n),
+                  "z": rng.normal(0, 0.3, n), "px": rng.normal(0, pscale, n),
+                  "py": rng.normal(0, pscale, n), "pz": rng.normal(0, pscale, n),
+                  "w": rng.uniform(0.5, 1.5, n)}
+        arrays["g_inv"] = 1 / np.sqrt(1 + arrays["px"] ** 2 + arrays["py"] ** 2 + arrays["pz"] ** 2)
+        P = Particles({"charge": -1, "dt": 0.08}, comm)
+        set_particles(P, arrays)
+        P._exc_full_limit = 0                  # force the bounded queue
+        P.sort_parts(S)
+        return S, P
+
+    S, P = make(2.0)                           # ~40 % change cell: 48 k > n/4 + 4096
+    S.depose_currents([P], push_mode="half")
+    with pytest.raises(RuntimeError, match="changed cell"):
+        P.exception_workspace()
+    S, P = make(0.02)                          # slow particles: a few per cent
+    S1 = Solver(dict(cfg), comm)
+    S.depose_currents([P], push_mode="half")
+    P.exception_workspace()                    # no overflow -> no exception
