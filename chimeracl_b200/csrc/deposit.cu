@@ -6,15 +6,16 @@
 //   treat_axis_*, divide_by_dv_*, warp_axis_*  kernels/grid_generic.cl:4-86
 //
 // Design (HBM-bound FP64 scatter-add, not GEMM-shaped):
-//   * one CTA owns kDepCells consecutive cells = one contiguous range of the
-//     cell-sorted particle list (cell_offset), processed in batches;
+//   * one CTA owns CELLS consecutive cells = one contiguous range of the cell-sorted
+//     particle list (cell_offset), processed in batches (one batch in the 32-cell
+//     geometry used for the current, see DepGeom);
 //   * stage (thread per particle, through sort_indx): the attributes are copied
-//     global->shared ASYNCHRONOUSLY (cp.async, double buffered) while the previous
-//     batch is being accumulated; on arrival the owning thread converts them in
-//     place (sqrt, 1/r, scaled coordinates), once per particle;
-//   * phase 2 (thread per cell and component): accumulate the cell's 2x2 node
-//     stencil for all modes in registers from shared memory (padded layout, no
-//     bank conflicts for ~uniform fillings) -- no atomics at all inside a cell;
+//     global->shared ASYNCHRONOUSLY (cp.async); on arrival the owning thread converts
+//     them in place (sqrt, 1/r, scaled coordinates), once per particle -- and, in the
+//     fused variants, pushes the coordinates and computes the next cell index;
+//   * accumulate (thread per cell and component): the cell's 2x2 node stencil for all
+//     modes in registers from shared memory (padded layout, no bank conflicts for
+//     ~uniform fillings) -- no atomics at all inside a cell;
 //   * one FP64 RED per node value and CELL (not per particle) to the L2.
 // The four colour passes, their launches and the memsets between them are gone;
 // sums agree with the reference up to FP64 summation order.
@@ -28,7 +29,7 @@ namespace chb {
 //   128 cells, batches of 512 particles, double buffered (the staging of batch b+1
 //        overlaps the accumulation of batch b; per batch only the warps owning its ~32
 //        cells accumulate, the others wait at the barrier);
-//    32 cells, ONE batch of up to 640 particles, single buffer: no CTA-wide pipeline at
+//    32 cells, ONE batch of up to 544 particles, single buffer: no CTA-wide pipeline at
 //        all -- every warp of the CTA accumulates at the same time, and the overlap of
 //        loads and arithmetic comes from the many small CTAs resident on an SM.
 template <int CELLS>
