@@ -91,11 +91,17 @@ class PIC_loop:
 
         for solver in self.solvers:
             self.timer_start()
-            if hasattr(solver, 'finish_currents'):
-                solver.finish_currents()       # J: all-reduce (multi-GPU) + axis / dV
             multi = getattr(solver.comm, 'process_group', None) is not None and \
                 hasattr(solver, 'finish_charge')
-            solver.depose_charge(species=self.species, **({'defer': True} if multi else {}))
+            if multi:
+                # the sum of J over the ranks (started right after the one-pass particle
+                # side) keeps running under the scan + scatter AND the charge deposits
+                solver.depose_charge(species=self.species, defer=True)
+                solver.finish_currents()       # J: wait for the all-reduce, axis / dV
+            else:
+                if hasattr(solver, 'finish_currents'):
+                    solver.finish_currents()
+                solver.depose_charge(species=self.species)
             self.timer_record('depose')
 
             # forward transform with the spectral smoothing (reference: a separate
