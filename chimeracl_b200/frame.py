@@ -4,6 +4,9 @@ import numpy as np
 
 class Frame():
     def __init__(self, configs_in, comm=None):
+        self._process_configs(configs_in)
+
+    def _process_configs(self, configs_in):
         self.Args = configs_in
         for key, default in (('Steps', 1.), ('Velocity', 0.), ('dt', 1),
                              ('DensityProfiles', None)):

@@ -198,6 +198,29 @@ class TransformerMethodsCL(GenericMethodsCL):
                     self._fft_rows(spec, tmp, 1, phs, out_real=real)
                     self._dot_batched(grid, D['DHT_inv_m' + ms], tmp)
 
+    # the reference's per-component helpers (transformer_methods_cl.py:290-455); kept
+    # as entry points with the reference signature, served by the batched path above
+    def _split_names(self, dht_arg, arg_in, arg_out, forward):
+        grid, spec = (arg_in, arg_out) if forward else (arg_out, arg_in)
+        comp = grid[:-2]
+        want = 'DHT_m' if forward else 'DHT_inv_m'
+        if not (grid.endswith('_m') and spec == comp + '_fb_m' and dht_arg == want):
+            raise ValueError("chimera_b200: unsupported array naming in transform helper: "
+                             "%s, %s, %s" % (dht_arg, arg_in, arg_out))
+        return comp
+
+    def _transform_forward(self, dht_arg, arg_in, arg_out, phs_shft=None):
+        self.transform_fields([self._split_names(dht_arg, arg_in, arg_out, True)], 0, 'full')
+
+    def _transform_backward(self, dht_arg, arg_in, arg_out, phs_shft=None):
+        self.transform_fields([self._split_names(dht_arg, arg_in, arg_out, False)], 1, 'full')
+
+    def _half_transform_forward(self, dht_arg, arg_in, arg_out, phs_shft=None):
+        self.transform_fields([self._split_names(dht_arg, arg_in, arg_out, True)], 0, 'half')
+
+    def _half_transform_backward(self, dht_arg, arg_in, arg_out, phs_shft=None):
+        self.transform_fields([self._split_names(dht_arg, arg_in, arg_out, False)], 1, 'half')
+
     # ------------------------------------------------------------------ spectral operators
     def field_poiss_vec(self, fld):
         for m in range(self.Args['M'] + 1):

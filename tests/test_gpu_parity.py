@@ -707,3 +707,29 @@ def test_cell_changer_queue_overflow_is_detected(comm):
     S1 = Solver(dict(cfg), comm)
     S.depose_currents([P], push_mode="half")
     P.exception_workspace()                    # no overflow -> no exception
+
+
+def test_reference_named_transform_helpers(comm):
+    """The reference's per-component helpers (_transform_forward / _backward and the
+    half variants, transformer_methods_cl.py:290-455) exist with its signature and give
+    what transform_field gives; unknown array namings are refused loudly."""
+    from chimeracl_b200.solver import Solver
+    cfg = {"Xmin": -1.0, "Xmax": 1.0, "Nx": 64, "Rmin": 0.0, "Rmax": 1.0, "Nr": 24, "M": 1}
+    S1, S2 = Solver(dict(cfg), comm), Solver(dict(cfg), comm)
+    rng = np.random.default_rng(31)
+    a0 = rng.normal(size=(24, 64))
+    a1 = rng.normal(size=(24, 64)) + 1j * rng.normal(size=(24, 64))
+    for S in (S1, S2):
+        S.DataDev["rho_m0"][:] = a0
+        S.DataDev["rho_m1"][:] = a1
+    S1.transform_field("rho", 0, "full")
+    S2._phase(0)
+    S2._transform_forward("DHT_m", "rho_m", "rho_fb_m", S2.DataDev["phs_shft"])
+    for m in "01":
+        assert np.array_equal(S1.DataDev["rho_fb_m" + m].get(), S2.DataDev["rho_fb_m" + m].get())
+    S1.transform_field("rho", 1, "half")
+    S2._half_transform_backward("DHT_inv_m", "rho_fb_m", "rho_m", None)
+    for m in "01":
+        assert np.array_equal(S1.DataDev["rho_m" + m].get(), S2.DataDev["rho_m" + m].get())
+    with pytest.raises(ValueError):
+        S2._transform_forward("DHT_m", "rho_m", "Jx_fb_m", None)
