@@ -58,7 +58,8 @@ def build(force=False, verbose=False):
         newest = max(os.path.getmtime(d) for d in _deps(src))
         if not force and os.path.exists(obj) and os.path.getmtime(obj) >= newest:
             continue
-        cmd = [nvcc] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + \
+        cmd = [nvcc] + ARCH + COMMON + extra + os.environ.get("CHB_NVCC_FLAGS", "").split() + \
+              (["-Xptxas", "-v"] if verbose else []) + \
               ["-c", src, "-o", obj]
         procs.append((name, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
     failed = False

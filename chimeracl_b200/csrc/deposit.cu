@@ -26,17 +26,23 @@
 namespace chb {
 
 // Two CTA geometries (template parameter CELLS):
-//   128 cells, batches of 512 particles, double buffered (the staging of batch b+1
+//   128 cells, batches of 512 (current) / 256 (charge) particles, double buffered (the staging of batch b+1
 //        overlaps the accumulation of batch b; per batch only the warps owning its ~32
 //        cells accumulate, the others wait at the barrier);
 //    32 cells, ONE batch of up to 544 particles, single buffer: no CTA-wide pipeline at
 //        all -- every warp of the CTA accumulates at the same time, and the overlap of
 //        loads and arithmetic comes from the many small CTAs resident on an SM.
-template <int CELLS>
+// charge deposit (128-cell geometry): 256-particle batches keep the double buffer at
+// 22 KB, so that 8 CTAs (32 warps, 63 registers) fit an SM -- measured 0.35 ms per call
+// against 0.42 (320 / 512 per batch) and 0.43 / 0.50 (192 / 128)
+#ifndef CHB_SCALAR_BATCH
+#define CHB_SCALAR_BATCH 256
+#endif
+template <int CELLS, bool VEC = true>
 struct DepGeom {
   static constexpr int kCells = CELLS;
   static constexpr bool kDouble = CELLS >= 128;
-  static constexpr int kBatch = kDouble ? 512 : CELLS * 17;
+  static constexpr int kBatch = kDouble ? (VEC ? 512 : CHB_SCALAR_BATCH) : CELLS * 17;
   static constexpr int kPad = kBatch + kBatch / 16;
 };
 
@@ -146,7 +152,7 @@ struct DepShape {
   static constexpr int kPerCell = VEC ? 3 : (kSplit ? 2 * M + 1 : 1);
   static constexpr int kThreads = CELLS * kPerCell;
   // resident CTAs the launch bounds ask for (registers per thread follow from it)
-  static constexpr int kCtas = CELLS >= 128 ? (VEC ? 3 : 6) : (VEC ? 6 : (M > 1 ? 5 : 8));
+  static constexpr int kCtas = CELLS >= 128 ? (VEC ? 3 : 8) : (VEC ? 6 : (M > 1 ? 5 : 8));
 };
 
 template <int M, bool VEC, int CELLS>
@@ -154,7 +160,7 @@ struct DepSmem {
   // staged doubles per particle: raw attributes land here asynchronously and are
   // converted in place to (ax, ar, wp, [px, py, pz], [e0, e1])
   static constexpr int kSlots = VEC ? 8 : 5;
-  static constexpr int kBytes = (DepGeom<CELLS>::kDouble ? 2 : 1) * kSlots * DepGeom<CELLS>::kPad *
+  static constexpr int kBytes = (DepGeom<CELLS, VEC>::kDouble ? 2 : 1) * kSlots * DepGeom<CELLS, VEC>::kPad *
                                 (int)sizeof(double);
 };
 
@@ -179,9 +185,9 @@ depose_kernel(const __grid_constant__ DepArgs<M, VEC> a) {
   constexpr int MM = M > 0 ? M : 1;
   constexpr int NS = DepSmem<M, VEC, CELLS>::kSlots;
   constexpr int kDepCells = CELLS;
-  constexpr int kDepBatch = DepGeom<CELLS>::kBatch;
-  constexpr int kDepPad = DepGeom<CELLS>::kPad;
-  constexpr bool DB = DepGeom<CELLS>::kDouble;
+  constexpr int kDepBatch = DepGeom<CELLS, VEC>::kBatch;
+  constexpr int kDepPad = DepGeom<CELLS, VEC>::kPad;
+  constexpr bool DB = DepGeom<CELLS, VEC>::kDouble;
   constexpr int KP = (kDepBatch + NT - 1) / NT;     // particles loaded per thread and batch
   // slot layout (VEC):   raw x y z px py pz w g_inv -> ax ar wp px py pz e0 e1
   // slot layout (!VEC):  raw x y z w  -          -> ax ar wp e0 e1
