@@ -215,19 +215,24 @@ sort_scatter_kernel(const uint32_t* __restrict__ indx_in_cell,
   const uint32_t n_round = ((n + 31u) / 32u) * 32u;
   const uint32_t stride = gridDim.x * kBlock * kIlp;
   // kIlp independent particles per thread: the slot-claiming atomics of all of them are
-  // in flight before the first result is needed
-  for (uint32_t base = blockIdx.x * kBlock * kIlp + threadIdx.x; base - lane < n_round;
+  // in flight before the first result is needed.  A warp owns kIlp CONSECUTIVE 32-particle
+  // chunks and claims them in order, so a cell whose particles straddle chunks of the same
+  // warp still receives them in ascending storage order (fewer segments for the fix-up
+  // to repair: 0.279 -> 0.266 ms for scatter + fix-up; correctness never depends on it).
+  constexpr uint32_t kStep = 32;
+  const uint32_t first = (threadIdx.x >> 5) * 32 * kIlp + lane;
+  for (uint32_t base = blockIdx.x * kBlock * kIlp + first; base - lane < n_round;
        base += stride) {
     uint32_t cell[kIlp], basev[kIlp];
     int head[kIlp], rank[kIlp];
 #pragma unroll
     for (int k = 0; k < kIlp; ++k) {
-      const uint32_t i = base + k * kBlock;
+      const uint32_t i = base + k * kStep;
       cell[k] = i < n ? indx_in_cell[i] : 0xffffffffu;
     }
 #pragma unroll
     for (int k = 0; k < kIlp; ++k) {
-      const uint32_t i = base + k * kBlock;
+      const uint32_t i = base + k * kStep;
       basev[k] = 0;
       head[k] = rank[k] = 0;
       if (i - lane < n_round) {            // warp-uniform
@@ -238,7 +243,7 @@ sort_scatter_kernel(const uint32_t* __restrict__ indx_in_cell,
     }
 #pragma unroll
     for (int k = 0; k < kIlp; ++k) {
-      const uint32_t i = base + k * kBlock;
+      const uint32_t i = base + k * kStep;
       if (i - lane < n_round) {
         const uint32_t b = __shfl_sync(0xffffffffu, basev[k], head[k]);
         if (i < n) sort_indx[b + rank[k]] = i;
