@@ -28,6 +28,7 @@ SIGNATURES = {
     "chb_depose_vector": (_i32, [_i32] + [_vp] * 10 + [_i32, _u32, _u32] + [_vp] * 4 + [_vp, _vp]),
     "chb_push_depose_vector": (_i32, [_i32] + [_vp] * 11 + [_u32, _i32, _u32, _u32] + [_vp] * 4 + [_vp, _vp, _sz, _vp]),
     "chb_fft_damp_x_batched": (_i32, [_vp, _vp, _i32, _u32, _u32, _sz, _vp, _vp, _vp, _u32, _vp, _vp]),
+    "chb_dht_tile_columns": (_i32, [_u32, _u32, _i32]),
     "chb_dmma_peak": (_i32, [_vp, _sz, _i32, _vp, _vp]),
     "chb_push_depose_workspace_bytes": (_sz, [_u32]),
     "chb_push_depose_push_index": (_i32, [_i32] + [_vp] * 11 + [_u32, _i32, _u32, _u32] + [_vp] * 4 + [_vp, _vp, _vp, _vp, _sz, _vp]),

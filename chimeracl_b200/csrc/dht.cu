@@ -445,6 +445,10 @@ static int dht_launch(const double* A, uint32_t lda, const double* const* Bv, in
   CHB_RETURN_LAST_ERROR();
 }
 
+extern "C" int chb_dht_tile_columns(uint32_t M, uint32_t N_doubles, int nbatch) {
+  return 16 * pick_wide_nt(M, N_doubles, nbatch < 1 ? 1 : nbatch);
+}
+
 extern "C" int chb_dht(const double* A, uint32_t lda, const double* B, uint32_t ldb,
                        double* C, uint32_t ldc, uint32_t M, uint32_t K, uint32_t N,
                        int is_complex, double alpha_re, double alpha_im, int accumulate,

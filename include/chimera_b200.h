@@ -229,6 +229,12 @@ int chb_psatd_advance(size_t n, const double* dt_inv_dev, const double* c1, cons
 
 /* ---------------------------------------------------------------- spectral: DHT and FFT */
 
+/* Host-only query (no GPU work): width in real columns (64..128, multiple of 16) of the
+ * 128-row output tiles the wide contraction kernel uses for an M x N_doubles result
+ * (N_doubles = 2*Nx for complex data) and `nbatch` right-hand sides -- the width whose tile
+ * count fills whole waves of the 148 SMs best.  No reference counterpart. */
+int chb_dht_tile_columns(uint32_t M, uint32_t N_doubles, int nbatch);
+
 /* Measurement aid (bench.py): launches a register-only FP64 DMMA loop on every SM;
  * flops_out = floating-point operations it executes (time it with events on `stream`).
  * scratch: >= 148*512 doubles of device memory.  No reference counterpart. */

@@ -110,3 +110,27 @@ def test_shard_range_partitions_everything():
             assert spans[0][0] == 0 and spans[-1][1] == n
             for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
                 assert a1 == b0 and a1 - a0 >= b1 - b0 >= 0
+
+
+def test_dht_tile_width_fills_whole_waves():
+    """chb_dht_tile_columns (host-only): the wide contraction kernel picks, per launch,
+    the tile width whose tile count wastes the least of the 148-SM waves.  cfg3 (Nr=512,
+    Nx=4096): 112 columns -> exactly 148 tiles (real) / 296 (complex) per contraction."""
+    from chimeracl_b200 import _lib
+    lib = _lib.load()
+    rows = 511
+
+    def waste(width, n, nbatch):
+        tiles = -(-n // width) * -(-rows // 128) * nbatch
+        waves = -(-tiles // 148)
+        return waves * width
+
+    for n, nbatch in ((4096, 1), (8192, 1), (4096, 4), (8192, 6), (32768, 3), (1800, 1)):
+        w = lib.chb_dht_tile_columns(rows, n, nbatch)
+        assert w in (64, 80, 96, 112, 128)
+        assert waste(w, n, nbatch) == min(waste(c, n, nbatch) for c in (64, 80, 96, 112, 128))
+    assert lib.chb_dht_tile_columns(rows, 4096, 1) == 112
+    assert lib.chb_dht_tile_columns(rows, 8192, 1) == 112
+    assert -(-8192 // 112) * 4 == 296          # two full waves
+    # the worst-case queue of the one-pass particle side: one 64-byte record per particle
+    assert lib.chb_push_depose_workspace_bytes(1000) == 16 + 64 * 1000
