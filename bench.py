@@ -370,7 +370,8 @@ def run_ours(args):
         # reference; 3 of the complex ones are obtained here from a mirror identity
         Mm = A["M"]
         n_real, n_cplx = (10, 19) if Mm == 1 else ((10, 0) if Mm == 0 else (10, 35))
-        n_cplx_exec = n_cplx - (3 if Mm >= 1 else 0)
+        # ... and the two contractions of m = 0 sources run on half of the kx columns
+        n_cplx_exec = n_cplx - (3 if Mm >= 1 else 0) - (1 if Mm >= 1 and loop.real_m0_symmetry else 0)
         flops = (0.5 * n_real + n_cplx) * flop_c
         flops_exec = (0.5 * n_real + n_cplx_exec) * flop_c
         dht_ms = sum(kernels[k]["ms_per_step"] for k in dht_names)

@@ -50,6 +50,8 @@ SIGNATURES = {
     "chb_dht": (_i32, [_vp, _u32, _vp, _u32, _vp, _u32, _u32, _u32, _u32, _i32, _dbl, _dbl, _i32, _vp]),
     "chb_dht2": (_i32, [_vp, _u32, _vp, _u32, _vp, _dbl, _dbl, _i32, _vp, _dbl, _dbl, _i32,
                         _u32, _u32, _u32, _u32, _i32, _vp]),
+    "chb_dht2_hermitian": (_i32, [_vp, _u32, _vp, _u32, _vp, _dbl, _dbl, _i32, _vp, _dbl, _dbl, _i32,
+                                  _u32, _u32, _u32, _u32, _vp]),
     "chb_dht_batched": (_i32, [_vp, _u32, _vp, _vp, _i32, _u32, _u32, _u32, _u32, _u32, _i32, _vp]),
     "chb_fft_x_batched": (_i32, [_vp, _vp, _i32, _u32, _u32, _sz, _sz, _i32, _i32, _i32, _vp, _i32,
                                  _vp, _u32, _vp, _vp, _vp, _vp]),

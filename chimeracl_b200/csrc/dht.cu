@@ -47,6 +47,10 @@ struct GemmArgs {
   uint32_t ldc2;
   double alpha2_re, alpha2_im;
   int accumulate2;
+  // > 0 (complex data, wide kernel only): B is the x-spectrum of a REAL field, i.e.
+  // B(:, Nx-k) = conj(B(:, k)); only the columns k <= Nx/2 are contracted (N is set
+  // accordingly) and every result is also written, conjugated, to column Nx-k
+  uint32_t mirror_nx;
 };
 
 constexpr int kSlabDoubles = BM * LDA_S + BK * LDB_S;
@@ -320,6 +324,17 @@ dht_gemm_wide_kernel(const __grid_constant__ GemmArgs p) {
       if (p.C2)
         gemm_store(p.C2 + (size_t)row * p.ldc2 + col, acc[i][j][0], acc[i][j][1], p.alpha2_re,
                    p.alpha2_im, p.complex_pairs, p.accumulate2, pair);
+      if (p.mirror_nx) {
+        const uint32_t k = col >> 1;                     // complex column
+        if (k > 0 && 2 * k < p.mirror_nx) {
+          const uint32_t mcol = 2 * (p.mirror_nx - k);
+          gemm_store(Cg + (size_t)row * p.ldc + mcol, acc[i][j][0], -acc[i][j][1], p.alpha_re,
+                     p.alpha_im, 1, p.accumulate, true);
+          if (p.C2)
+            gemm_store(p.C2 + (size_t)row * p.ldc2 + mcol, acc[i][j][0], -acc[i][j][1],
+                       p.alpha2_re, p.alpha2_im, 1, p.accumulate2, true);
+        }
+      }
     }
   }
 }
@@ -388,7 +403,7 @@ static int dht_launch(const double* A, uint32_t lda, const double* const* Bv, in
                       uint32_t N,
                       int is_complex, double alpha_re, double alpha_im, int accumulate,
                       double* C2, uint32_t ldc2, double alpha2_re, double alpha2_im,
-                      int accumulate2, void* stream) {
+                      int accumulate2, void* stream, int hermitian = 0) {
   if (M == 0 || N == 0 || nbatch == 0) return CHB_OK;
   if (nbatch < 0 || nbatch > CHB_MAX_FIELDS || (C2 && nbatch != 1)) return CHB_ERR_ARG;
   if (!is_complex && (alpha_im != 0.0 || alpha2_im != 0.0)) return CHB_ERR_ARG;
@@ -410,6 +425,7 @@ static int dht_launch(const double* A, uint32_t lda, const double* const* Bv, in
   p.alpha_re = alpha_re; p.alpha_im = alpha_im;
   p.complex_pairs = is_complex;
   p.accumulate = accumulate;
+  p.mirror_nx = 0;
   dim3 grid((p.N + BN - 1) / BN, (M + BM - 1) / BM, nbatch);
   static bool attr_set = false;
   if (!attr_set) {
@@ -427,6 +443,10 @@ static int dht_launch(const double* A, uint32_t lda, const double* const* Bv, in
              (reinterpret_cast<uintptr_t>(A) % 16 == 0) && (p.lda > p.K || p.K % 2 == 0);
   for (int k = 0; k < nbatch && vec; ++k) vec = reinterpret_cast<uintptr_t>(Bv[k]) % 16 == 0;
   const bool wide = vec && (p.ldc % 2 == 0) && (!C2 || p.ldc2 % 2 == 0) && !getenv("CHB_DHT_NARROW");
+  if (wide && hermitian && is_complex && N >= 4 && N % 2 == 0) {
+    p.mirror_nx = N;                 // complex columns of the full result
+    p.N = 2 * (N / 2 + 1);           // contracted: k = 0 .. Nx/2
+  }
   if (wide) {
     cudaError_t e;
     switch (pick_wide_nt(M, p.N, nbatch)) {
@@ -462,6 +482,14 @@ extern "C" int chb_dht_batched(const double* A, uint32_t lda, const double* cons
                                uint32_t M, uint32_t K, uint32_t N, int is_complex, void* stream) {
   return dht_launch(A, lda, B_host, nbatch, ldb, C_host, ldc, M, K, N, is_complex, 1.0, 0.0, 0,
                     nullptr, 0, 1.0, 0.0, 0, stream);
+}
+
+extern "C" int chb_dht2_hermitian(const double* A, uint32_t lda, const double* B, uint32_t ldb,
+                                  double* C1, double a1_re, double a1_im, int accumulate1,
+                                  double* C2, double a2_re, double a2_im, int accumulate2,
+                                  uint32_t ldc, uint32_t M, uint32_t K, uint32_t N, void* stream) {
+  return dht_launch(A, lda, &B, 1, ldb, &C1, ldc, M, K, N, 1, a1_re, a1_im, accumulate1, C2, ldc,
+                    a2_re, a2_im, accumulate2, stream, 1);
 }
 
 extern "C" int chb_dht2(const double* A, uint32_t lda, const double* B, uint32_t ldb,

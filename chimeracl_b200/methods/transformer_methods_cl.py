@@ -113,10 +113,16 @@ class TransformerMethodsCL(GenericMethodsCL):
     def _cdot(self, c, a, b):
         self._dot(c, a, b)
 
-    def _cdot2(self, a, b, c1, alpha1, acc1, c2, alpha2, acc2):
+    def _cdot2(self, a, b, c1, alpha1, acc1, c2, alpha2, acc2, hermitian=False):
         M, K = a.shape
         N = b.shape[1]
         a1, a2 = complex(alpha1), complex(alpha2)
+        if hermitian:
+            # b is the x-spectrum of a real field: half of the columns are contracted
+            self._call('chb_dht2_hermitian', a.ptr, a.t.stride(0), b.ptr, b.t.stride(0), c1.ptr,
+                       a1.real, a1.imag, int(acc1), c2.ptr, a2.real, a2.imag, int(acc2),
+                       c1.t.stride(0), M, K, N)
+            return
         self._call('chb_dht2', a.ptr, a.t.stride(0), b.ptr, b.t.stride(0), c1.ptr, a1.real,
                    a1.imag, int(acc1), c2.ptr, a2.real, a2.imag, int(acc2), c1.t.stride(0),
                    M, K, N, 1)
@@ -244,6 +250,15 @@ class TransformerMethodsCL(GenericMethodsCL):
         self._call('chb_mirror_axpy', out.ptr, b.ptr, alpha.real, alpha.imag, beta.real,
                    beta.imag, int(accumulate), b.size, int(self.Args['Nx']))
 
+    def _m0_real(self):
+        """True while the caller vouches that the m = 0 spectral arrays are spectra of REAL
+        grid fields (F(kr, -kx) = conj F(kr, kx)), which lets the contractions of m = 0
+        sources run on half of the kx columns.  PIC_loop.step() sets it for its own calls
+        (its m = 0 spectra are FFTs of real arrays, and damp_fields projects E and G onto
+        real x-space fields every step); the reference API itself accepts arbitrary
+        complex m = 0 spectra, so the default is False."""
+        return bool(self.__dict__.get('m0_spectra_of_real_fields', False))
+
     def _m0_pm_identical(self):
         """dDHT_minus_m0 == dDHT_plus_m0 (jn_zeros(-1, n) == jn_zeros(1, n)): then
         D.F_{-1} = -conj(mirror(D.F_{+1})) and the m=0 'minus' contractions are free."""
@@ -279,7 +294,8 @@ class TransformerMethodsCL(GenericMethodsCL):
                 self.set_to(oz, 0.)
                 continue
             # oy = -b, oz = -i b with b = dDHT_minus . src
-            self._cdot2(D['dDHT_minus_m' + str(m)], src, oy, -1., False, oz, -1.j, False)
+            self._cdot2(D['dDHT_minus_m' + str(m)], src, oy, -1., False, oz, -1.j, False,
+                        hermitian=(m == 1 and self._m0_real()))
             if m < M:
                 # oy += b, oz -= i b with b = dDHT_plus . scl_{m+1}
                 self._cdot2(D['dDHT_plus_m' + str(m)], D[scl_in + '_fb_m' + str(m + 1)],
@@ -336,7 +352,8 @@ class TransformerMethodsCL(GenericMethodsCL):
             dm = D['dDHT_minus_m' + str(m)]
             self.axpbyz(-1, fz, 1.j, fy, D['fld_buff0_c'])
             self._dot(ox, dm, D['fld_buff0_c'])                       # ox  = dDHT-.(-fz + i fy)
-            self._cdot2(dm, fx, oy, -1.j, True, oz, 1., True)         # oy -= i b, oz += b
+            self._cdot2(dm, fx, oy, -1.j, True, oz, 1., True,         # oy -= i b, oz += b
+                        hermitian=(m == 1 and self._m0_real()))
             if m < M:
                 fx, fy, fz = (D[fld_in + c + '_fb_m' + str(m + 1)] for c in 'xyz')
                 dp = D['dDHT_plus_m' + str(m)]

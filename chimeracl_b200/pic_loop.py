@@ -15,7 +15,7 @@ loop_steps = ['frame', 'push-x', 'sort', 'depose',
 
 class PIC_loop:
     def __init__(self, solvers=[], species=[], frames=[], diags=[], timit=False,
-                 fuse_push_sort=True):
+                 fuse_push_sort=True, real_m0_symmetry=True):
         self.solvers = solvers
         self.mainsolver = self.solvers[0]
         self.species = species
@@ -24,6 +24,7 @@ class PIC_loop:
         self.timit = timit
         self.it = 0
         self.fuse_push_sort = bool(fuse_push_sort)
+        self.real_m0_symmetry = bool(real_m0_symmetry)
         if self.timit is True:
             self.Timer = {key: 0 for key in loop_steps}
             self._events = []
@@ -126,6 +127,9 @@ class PIC_loop:
                         solver.DataDev['dN1' + key], solver.DataDev['dN0' + key]
             self.timer_record('data_copy')
 
+            # the m = 0 spectra of this loop are spectra of real grid fields: their
+            # contractions run on half of the kx columns (see Transformer._m0_real)
+            solver.m0_spectra_of_real_fields = self.real_m0_symmetry
             self.timer_start()
             solver.field_grad('rho', 'dN1')
             self.timer_record('grad')
@@ -142,6 +146,7 @@ class PIC_loop:
             solver.restore_B_fb()
             self.timer_record('restore_B')
 
+            solver.m0_spectra_of_real_fields = False
             self.timer_start()
             solver.fb_transform(vects=['E', 'B'], dir=1)
             self.timer_record('transform')

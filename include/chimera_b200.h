@@ -267,6 +267,16 @@ int chb_dht2(const double* A, uint32_t lda, const double* B, uint32_t ldb, doubl
              double a2_im, int accumulate2, uint32_t ldc, uint32_t M, uint32_t K, uint32_t N,
              int is_complex, void* stream);
 
+/* chb_dht2 for a complex B that is the x-spectrum of a REAL field (an m = 0 spectral
+ * array: B(:, Nx-k) = conj(B(:, k))): only the columns k <= Nx/2 are contracted, every
+ * result is also written, conjugated (before alpha), to column Nx-k.  Same results as
+ * chb_dht2 up to the rounding-level asymmetry of B; half the arithmetic.  The caller
+ * vouches for the symmetry (PIC_loop does: its m = 0 spectra come from real grid fields). */
+int chb_dht2_hermitian(const double* A, uint32_t lda, const double* B, uint32_t ldb,
+                       double* C1, double a1_re, double a1_im, int accumulate1, double* C2,
+                       double a2_re, double a2_im, int accumulate2, uint32_t ldc, uint32_t M,
+                       uint32_t K, uint32_t N, void* stream);
+
 /* Batched FFT along x of `rows` rows of length Nx (numpy conventions; inverse is
  * normalised).  Strides are in elements of the row's type.  in_real: input rows are
  * real; out_real: keep only the real part.  phase (Nx complex, may be NULL) multiplies

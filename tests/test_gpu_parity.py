@@ -733,3 +733,30 @@ def test_reference_named_transform_helpers(comm):
         assert np.array_equal(S1.DataDev["rho_m" + m].get(), S2.DataDev["rho_m" + m].get())
     with pytest.raises(ValueError):
         S2._transform_forward("DHT_m", "rho_m", "Jx_fb_m", None)
+
+
+def test_hermitian_contraction_matches_full(comm):
+    """chb_dht2_hermitian (columns k <= Nx/2 contracted, the rest mirrored) against
+    chb_dht2 on the spectrum of a real field, with complex alphas, accumulate on one
+    output and not on the other."""
+    from chimeracl_b200.solver import Solver
+    cfg = {"Xmin": -1.0, "Xmax": 1.0, "Nx": 256, "Rmin": 0.0, "Rmax": 1.0, "Nr": 41, "M": 1}
+    S = Solver(dict(cfg), comm)
+    rng = np.random.default_rng(17)
+    K, Nx = 40, 256
+    spec = np.fft.fft(rng.normal(size=(K, Nx)), axis=1)            # Hermitian in kx
+    b = S.DataDev["rho_fb_m0"]
+    b[:] = spec
+    outs = {}
+    for herm in (False, True):
+        c1, c2 = S.DataDev["dN1y_fb_m1"], S.DataDev["dN1z_fb_m1"]
+        c1[:] = np.zeros((K, Nx), complex)
+        c2[:] = np.full((K, Nx), 0.5 - 0.25j)
+        S._cdot2(S.DataDev["dDHT_minus_m1"], b, c1, -1.0, False, c2, -1.0j, True, hermitian=herm)
+        outs[herm] = (c1.get().copy(), c2.get().copy())
+    for k in range(2):
+        full, half = outs[False][k], outs[True][k]
+        assert rel_err(half, full) < 1e-13, k
+    # the mirrored half really is the conjugate image (before alpha): c1 = -A.b
+    c1 = outs[True][0]
+    assert np.allclose(c1[:, 1:Nx // 2], np.conj(c1[:, :Nx // 2:-1]), rtol=0, atol=1e-12 * np.abs(c1).max())
