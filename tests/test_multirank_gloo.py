@@ -53,6 +53,18 @@ def _worker(rank, world, port, out_dir):
                         S.Args, flds_r)
     tensors = [torch.from_numpy(a) for a in arrays]   # share memory with the arrays
     allreduce_sum(tensors, pg)
+    # the asynchronous flavour PIC_loop uses for the packed J / rho buffers: two sums in
+    # flight at once (J under the charge deposits, rho under the J transform), waited for
+    # in the order they were started
+    from chimeracl_b200.parallel import allreduce_sum_async
+    flat_j = torch.full((1000,), float(rank + 1), dtype=torch.float64)
+    flat_r = torch.arange(50, dtype=torch.float64) * (rank + 1)
+    wj = allreduce_sum_async(flat_j, pg)
+    wr = allreduce_sum_async(flat_r, pg)
+    wj.wait()
+    wr.wait()
+    assert torch.all(flat_j == world * (world + 1) / 2)
+    assert torch.equal(flat_r, torch.arange(50, dtype=torch.float64) * (world * (world + 1) / 2))
     for n in names:
         S.postproc_depose(n)
     if rank == 0:
