@@ -24,11 +24,23 @@
 
 namespace chb {
 
-constexpr int kGatCells = 64;                 // max cells per tile
+// mean filling of a tile's particle slots the tile width aims at (measured on cfg3:
+// 0.80 -> 0.979 ms, 0.90 -> 0.936, 0.98 -> 0.905, 1.0 -> 0.935; tiles that end up with more
+// particles than slots finish the remainder through the synchronous path)
+#ifndef CHB_GAT_FILL
+#define CHB_GAT_FILL 0.97
+#endif
+#ifndef CHB_GAT_CELLS
+#define CHB_GAT_CELLS 64
+#endif
+#ifndef CHB_GAT_SLOTS
+#define CHB_GAT_SLOTS 2
+#endif
+constexpr int kGatCells = CHB_GAT_CELLS;      // max cells per tile
 constexpr int kGatCols = kGatCells + 1;
 constexpr int kGatThreads = 512;
 constexpr int kGatCtasPerSm = 1;              // persistent CTAs per SM (2 x 256 threads measured slower)
-constexpr int kGatSlots = 2;                  // pipelined particles per thread and tile
+constexpr int kGatSlots = CHB_GAT_SLOTS;      // pipelined particles per thread and tile
 constexpr int kGatRound = kGatSlots * kGatThreads;
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
@@ -322,7 +334,7 @@ static int launch_gather(const double* x, const double* y, const double* z, doub
   // tile width from the mean filling, so that a tile's particles fit one pipelined round
   const double ncells = (double)(g.Nx - 1) * (double)(g.Nr - 1);
   const double ppc = ncells > 0 ? (double)np / ncells : 1.0;
-  uint32_t cpt = (uint32_t)(0.8 * kGatRound / (ppc > 1e-9 ? ppc : 1e-9));
+  uint32_t cpt = (uint32_t)(CHB_GAT_FILL * kGatRound / (ppc > 1e-9 ? ppc : 1e-9));
   if (cpt > (uint32_t)kGatCells) cpt = kGatCells;
   if (cpt < 4) cpt = 4;
   a.cells_per_tile = cpt;
