@@ -179,9 +179,15 @@ dht_gemm_kernel(GemmArgs p) {
 // (just under) a multiple of the 148 SMs: for Nx = 4096 a 112-wide tile gives exactly 148
 // (real) / 296 (complex) tiles per contraction, i.e. whole waves, where the 128 x 64 tiles
 // above ran 1.73 waves.  Needs 16-byte aligned operands (see dht_launch).
-constexpr int kWideStages = 3;
+#ifndef CHB_DHT_STAGES
+#define CHB_DHT_STAGES 3
+#endif
+#ifndef CHB_DHT_WBK
+#define CHB_DHT_WBK 32
+#endif
+constexpr int kWideStages = CHB_DHT_STAGES;
 constexpr int kWideThreads = 512;      // 16 warps: 8 (M) x 2 (N)
-constexpr int WBK = 32;                // k-slab of the wide kernel
+constexpr int WBK = CHB_DHT_WBK;       // k-slab of the wide kernel
 constexpr int WLDA = WBK + 4;          // 36: (g*36 + t) mod 16 distinct over a half warp
 
 __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gmem_src, bool valid) {
@@ -228,7 +234,7 @@ dht_gemm_wide_kernel(const __grid_constant__ GemmArgs p) {
 #pragma unroll
   for (int i = 0; i < kAPer; ++i) {
     const int c = tid + i * kWideThreads;
-    const int row = c >> 4, kc = (c & 15) * 2;
+    const int row = c / (WBK / 2), kc = (c % (WBK / 2)) * 2;
     a_ok[i] = m0 + row < p.M;
     a_src[i] = p.A + (size_t)(a_ok[i] ? m0 + row : 0) * p.lda + kc;
     a_dst[i] = row * WLDA + kc;

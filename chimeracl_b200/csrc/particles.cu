@@ -260,7 +260,10 @@ sort_scatter_kernel(const uint32_t* __restrict__ indx_in_cell,
 //   n <= kSmall      : per-thread insertion sort (input is a few ascending runs)
 //   n <= kFixCap     : CTA-wide bitonic network (arbitrary n)
 //   n >  kFixCap     : queued for sort_giant_kernel (single-CTA LSD radix sort)
-constexpr int kFixBlock = 256;   // cells per CTA, one thread per cell
+#ifndef CHB_FIX_BLOCK
+#define CHB_FIX_BLOCK 256
+#endif
+constexpr int kFixBlock = CHB_FIX_BLOCK;   // cells per CTA, one thread per cell
 constexpr int kFixCap = 8192;    // staged entries (32 KiB)
 constexpr int kSmall = 48;
 
