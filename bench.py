@@ -266,6 +266,12 @@ def run_ours(args):
         p.sort_parts(solver)
         p.align_parts()
     np_gpu = int(eons.Args["Np"])
+    # opt-in (validated on CPU/gloo and by the virtual-shard GPU test; not yet timed on
+    # NVLink): kr-row sharded field solve instead of the replicated one
+    shard_solve = world > 1 and (args.shard_spectral or
+                                 os.environ.get("CHB_SHARD_SPECTRAL", "0") == "1")
+    if shard_solve:
+        solver.enable_spectral_sharding()
     loop = PIC_loop(solvers=[solver], species=[eons, ions])
 
     def barrier():
@@ -454,7 +460,10 @@ def run_ours(args):
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": bench_config(A, np_gpu, world),
+            "config": dict(bench_config(A, np_gpu, world),
+                           **({"field_solve": "kr rows sharded x%d (all-gather rho/G spectra, "
+                                              "all-reduce E/B partials)" % world}
+                              if shard_solve else {})),
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e_value, "unit": "particle-steps/s",
                     "h2d_bytes_per_step": bytes_io[0], "d2h_bytes_per_step": bytes_io[1],
@@ -489,6 +498,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--small", action="store_true", help="debug-size grid (not a bench config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard-spectral", action="store_true",
+                    help="N>1: kr-row sharded field solve (Solver.enable_spectral_sharding)")
     args = ap.parse_args()
     if args.impl == "reference":
         if int(os.environ.get("RANK", "0")) != 0:

@@ -32,14 +32,21 @@ class SolverMethodsCL(GenericMethodsCL):
         self.Args['dont_send'].append('DampCells')
 
     def advance_fields(self, vecs):
+        """Element-wise in (kr, kx): with a kr-row sharded solve (transformer_methods_cl.py)
+        only the owned rows are advanced."""
         D = self.DataDev
         comps = self.Args['vec_comps']
+        own = self._own
+        if self._shard_is_empty():
+            return
         for m in range(self.Args['M'] + 1):
             ms = '_m' + str(m)
-            groups = [_lib.ptr_array([D[v + c + '_fb' + ms].ptr for c in comps]) for v in vecs]
-            self._call('chb_psatd_advance', int(self.Args['NxNrm1']), D['dt_inv'].ptr,
-                       D['MxSlv_cos(wdt)' + ms].ptr, D['MxSlv_sin(wdt)*w' + ms].ptr,
-                       D['MxSlv_1/w**2' + ms].ptr, *groups)
+            groups = [_lib.ptr_array([own(D[v + c + '_fb' + ms]).ptr for c in comps])
+                      for v in vecs]
+            c1 = own(D['MxSlv_cos(wdt)' + ms])
+            self._call('chb_psatd_advance', int(c1.size), D['dt_inv'].ptr,
+                       c1.ptr, own(D['MxSlv_sin(wdt)*w' + ms]).ptr,
+                       own(D['MxSlv_1/w**2' + ms]).ptr, *groups)
 
     def damp_fields_fused(self, flds):
         """The three calls of damp_fields (reference solver.py:32-35) as one in-place,
@@ -54,14 +61,16 @@ class SolverMethodsCL(GenericMethodsCL):
         if getattr(self, '_fft_L', None) != Nx:
             return False
         D = self.DataDev
+        if self._shard_is_empty():
+            return True
         phs_b, phs_f = self._phase(1), self._phase(0)
         arrays, real_x = [], []
         for fld in flds:
             for comp in self.Args['vec_comps']:
                 for m in range(self.Args['M'] + 1):
-                    arrays.append(D[fld + comp + '_fb_m' + str(m)])
+                    arrays.append(self._own(D[fld + comp + '_fb_m' + str(m)]))
                     real_x.append(1 if m == 0 else 0)
-        rows = int(self.Args['Nr']) - 1
+        rows = arrays[0].shape[0]            # Nr-1, or the owned kr rows
         for i in range(0, len(arrays), 16):
             chunk = arrays[i:i + 16]
             self._call('chb_fft_damp_x_batched', _lib.ptr_array([a.ptr for a in chunk]),
@@ -71,14 +80,19 @@ class SolverMethodsCL(GenericMethodsCL):
         return True
 
     def profile_edges(self, flds):
+        sh = self.__dict__.get('_shard')
+        if self._shard_is_empty():
+            return
         arrays = []
         for fld in flds:
             for comp in self.Args['vec_comps']:
                 for m in range(self.Args['M'] + 1):
-                    arrays.append(self.DataDev[fld + comp + '_m' + str(m)])
+                    a = self.DataDev[fld + comp + '_m' + str(m)]
+                    # sharded half transforms only hold the owned rows of grid[1:]
+                    arrays.append(a if sh is None else a[1 + sh.lo:1 + sh.hi])
         for i in range(0, len(arrays), 16):
             chunk = arrays[i:i + 16]
             self._call('chb_profile_edges', _lib.ptr_array([a.ptr for a in chunk]),
                        _lib.int_array([1 if a.dtype == np.complex128 else 0 for a in chunk]),
-                       len(chunk), self.DataDev['DampProfile'].ptr, int(self.Args['Nr']),
+                       len(chunk), self.DataDev['DampProfile'].ptr, int(chunk[0].shape[0]),
                        int(self.Args['Nx']), 2 * int(self.Args['DampCells']))

@@ -13,6 +13,15 @@ work is scheduled on the device:
   field_grad (:87-133), field_rot (:185-263): same operator algebra, with the
       "b = dDHT.x; y += a*b; z += c*b" triples folded into one two-output
       contraction (chb_dht2).
+
+kr-row sharding (multi-GPU field solve, no reference counterpart; see
+Solver.enable_spectral_sharding): while `self._shard` is set, every method here works on
+the kr rows [lo, hi) this rank owns -- element-wise work, FFTs (row-local) and the OUTPUT
+rows of the forward / grad / rot / div contractions (operator rows [lo, hi), full
+right-hand sides, which the caller all-gathers first) -- and the backward transform
+contracts over the owned rows only (operator columns [lo, hi)), leaving a partial sum in
+the grid arrays that the caller adds up over the ranks.  All of it is pointer arithmetic
+on the same C-ABI calls: a row block of a C-ordered array is contiguous.
 """
 import numpy as np
 
@@ -127,8 +136,13 @@ class TransformerMethodsCL(GenericMethodsCL):
                    a1.imag, int(acc1), c2.ptr, a2.real, a2.imag, int(acc2), c1.t.stride(0),
                    M, K, N, 1)
 
-    def _dot_batched(self, cs, a, bs):
-        """cs[k] = a . bs[k] for equally shaped right-hand sides, one launch."""
+    def _dot_batched(self, cs, a, bs, accumulate=False):
+        """cs[k] = a . bs[k] for equally shaped right-hand sides, one launch
+        (accumulate: cs[k] += ..., one launch per right-hand side)."""
+        if accumulate:
+            for c, b in zip(cs, bs):
+                self._dot(c, a, b, accumulate=True)
+            return
         cplx = bs[0].dtype == np.complex128
         M, K = a.shape
         N = bs[0].shape[1]
@@ -137,6 +151,22 @@ class TransformerMethodsCL(GenericMethodsCL):
             self._call('chb_dht_batched', a.ptr, a.t.stride(0),
                        _lib.ptr_array([x.ptr for x in bl]), _lib.ptr_array([x.ptr for x in cl]),
                        len(bl), bl[0].t.stride(0), cl[0].t.stride(0), M, K, N, int(cplx))
+
+    # ------------------------------------------------------------------ kr-row shard views
+    def _own(self, a):
+        """Rows of a (Nr-1, ...) spectral array / filter / operator matrix owned by the
+        current shard (the array itself when the solve is not sharded)."""
+        sh = self.__dict__.get('_shard')
+        return a if sh is None else a[sh.lo:sh.hi]
+
+    def _kcols(self, mat):
+        """Operator columns matching the owned rows of a right-hand side."""
+        sh = self.__dict__.get('_shard')
+        return mat if sh is None else mat[:, sh.lo:sh.hi]
+
+    def _shard_is_empty(self):
+        sh = self.__dict__.get('_shard')
+        return sh is not None and sh.hi <= sh.lo
 
     # ------------------------------------------------------------------ transforms
     def _phase(self, dir):
@@ -180,29 +210,41 @@ class TransformerMethodsCL(GenericMethodsCL):
         phs = self._phase(dir)
         full = (mode == 'full')
         n = len(comps)
+        own = self._own
+        sh = self.__dict__.get('_shard')
+        # sharded backward transform: the grid arrays receive this shard's partial sum
+        # (virtual shards of one process add to what the earlier ones left)
+        acc = sh is not None and not sh.first
         for m in range(self.Args['M'] + 1):
             ms = str(m)
             real = (m == 0)
             grid = [D[c + '_m' + ms][1:] for c in comps]
-            spec = [D[c + '_fb_m' + ms] for c in comps]
+            spec = [own(D[c + '_fb_m' + ms]) for c in comps]
+            if self._shard_is_empty():
+                if dir == 1 and full and not acc:
+                    for g in grid:
+                        g.fill(0.)
+                continue
             if dir == 0:
-                flt = D['SmoothingFilter_m' + ms] if smooth else None
+                flt = own(D['SmoothingFilter_m' + ms]) if smooth else None
                 if not full:
-                    self._fft_rows(grid, spec, 0, phs, in_real=real, out_filter=flt)
+                    self._fft_rows([own(g) for g in grid], spec, 0, phs, in_real=real,
+                                   out_filter=flt)
                 elif real:
-                    tmp = self._tmp('d', n)
-                    self._dot_batched(tmp, D['DHT_m0'], grid)
+                    tmp = [own(t) for t in self._tmp('d', n)]
+                    self._dot_batched(tmp, own(D['DHT_m0']), grid)
                     self._fft_rows(tmp, spec, 0, phs, in_real=True, out_filter=flt)
                 else:
-                    self._dot_batched(spec, D['DHT_m' + ms], grid)
+                    self._dot_batched(spec, own(D['DHT_m' + ms]), grid)
                     self._fft_rows(spec, spec, 0, phs, out_filter=flt)   # in place
             else:
                 if not full:
-                    self._fft_rows(spec, grid, 1, phs, out_real=real)
+                    self._fft_rows(spec, [own(g) for g in grid], 1, phs, out_real=real)
                 else:
-                    tmp = self._tmp('d' if real else 'c', n)
+                    tmp = [own(t) for t in self._tmp('d' if real else 'c', n)]
                     self._fft_rows(spec, tmp, 1, phs, out_real=real)
-                    self._dot_batched(grid, D['DHT_inv_m' + ms], tmp)
+                    self._dot_batched(grid, self._kcols(D['DHT_inv_m' + ms]), tmp,
+                                      accumulate=acc)
 
     # the reference's per-component helpers (transformer_methods_cl.py:290-455); kept
     # as entry points with the reference signature, served by the batched path above
@@ -229,21 +271,27 @@ class TransformerMethodsCL(GenericMethodsCL):
 
     # ------------------------------------------------------------------ spectral operators
     def field_poiss_vec(self, fld):
+        if self._shard_is_empty():
+            return
         for m in range(self.Args['M'] + 1):
             for comp in self.Args['vec_comps']:
-                self.mult_elementwise(self.DataDev['Poiss_m' + str(m)],
-                                      self.DataDev[fld + comp + '_fb_m' + str(m)])
+                self.mult_elementwise(self._own(self.DataDev['Poiss_m' + str(m)]),
+                                      self._own(self.DataDev[fld + comp + '_fb_m' + str(m)]))
 
     def field_poiss_scl(self, fld):
+        if self._shard_is_empty():
+            return
         for m in range(self.Args['M'] + 1):
-            self.mult_elementwise(self.DataDev['Poiss_m' + str(m)],
-                                  self.DataDev[fld + '_fb_m' + str(m)])
+            self.mult_elementwise(self._own(self.DataDev['Poiss_m' + str(m)]),
+                                  self._own(self.DataDev[fld + '_fb_m' + str(m)]))
 
     def fields_smooth(self, flds):
+        if self._shard_is_empty():
+            return
         for m in range(self.Args['M'] + 1):
             for fld in flds:
-                self.mult_elementwise(self.DataDev['SmoothingFilter_m' + str(m)],
-                                      self.DataDev[fld + '_fb_m' + str(m)])
+                self.mult_elementwise(self._own(self.DataDev['SmoothingFilter_m' + str(m)]),
+                                      self._own(self.DataDev[fld + '_fb_m' + str(m)]))
 
     def _mirror_axpy(self, out, b, alpha, beta, accumulate):
         alpha, beta = complex(alpha), complex(beta)
@@ -271,17 +319,22 @@ class TransformerMethodsCL(GenericMethodsCL):
         return flag
 
     def field_grad(self, scl_in, vec_out):
+        """Sharded solve: outputs and the element-wise source are the owned rows; the
+        contraction sources scl_in_fb_m* must be valid on ALL rows (all-gathered)."""
         D, M = self.DataDev, self.Args['M']
+        own = self._own
         fast0 = self._m0_pm_identical()
+        if self._shard_is_empty():
+            return
         if not fast0:
             self._get_mm1_scl(scl_in)
         for m in range(M + 1):
-            ox, oy, oz = (D[vec_out + c + '_fb_m' + str(m)] for c in 'xyz')
-            self.ab_dot_x(1.j, D['kx'], D[scl_in + '_fb_m' + str(m)], ox)
+            ox, oy, oz = (own(D[vec_out + c + '_fb_m' + str(m)]) for c in 'xyz')
+            self.ab_dot_x(1.j, D['kx'], own(D[scl_in + '_fb_m' + str(m)]), ox)
             if m == 0 and fast0:
                 # b+ = dDHT+ . scl_1 ; b- = dDHT- . scl_{-1} = -conj(mirror(b+))
-                bp = D['fld_buff0_c']
-                self._dot(bp, D['dDHT_plus_m0'], D[scl_in + '_fb_m1'])
+                bp = own(D['fld_buff0_c'])
+                self._dot(bp, own(D['dDHT_plus_m0']), D[scl_in + '_fb_m1'])
                 self._mirror_axpy(oy, bp, 1., 1., False)       # oy = -b- + b+
                 self._mirror_axpy(oz, bp, -1.j, 1.j, False)    # oz = -i b- - i b+
                 continue
@@ -294,20 +347,24 @@ class TransformerMethodsCL(GenericMethodsCL):
                 self.set_to(oz, 0.)
                 continue
             # oy = -b, oz = -i b with b = dDHT_minus . src
-            self._cdot2(D['dDHT_minus_m' + str(m)], src, oy, -1., False, oz, -1.j, False,
+            self._cdot2(own(D['dDHT_minus_m' + str(m)]), src, oy, -1., False, oz, -1.j, False,
                         hermitian=(m == 1 and self._m0_real()))
             if m < M:
                 # oy += b, oz -= i b with b = dDHT_plus . scl_{m+1}
-                self._cdot2(D['dDHT_plus_m' + str(m)], D[scl_in + '_fb_m' + str(m + 1)],
+                self._cdot2(own(D['dDHT_plus_m' + str(m)]), D[scl_in + '_fb_m' + str(m + 1)],
                             oy, 1., True, oz, -1.j, True)
 
     def field_div(self, vec_in, scl_out):
+        """Sharded solve: vec_in{y,z}_fb_m* must be valid on all rows (see field_grad)."""
         D, M = self.DataDev, self.Args['M']
+        own = self._own
+        if self._shard_is_empty():
+            return
         for comp in ['y', 'z']:
             self._get_mm1_scl(vec_in + comp, comp)
         for m in range(M + 1):
-            out = D[scl_out + '_fb_m' + str(m)]
-            self.ab_dot_x(1.j, D['kx'], D[vec_in + 'x' + '_fb_m' + str(m)], out)
+            out = own(D[scl_out + '_fb_m' + str(m)])
+            self.ab_dot_x(1.j, D['kx'], own(D[vec_in + 'x' + '_fb_m' + str(m)]), out)
             if m > 0:
                 fy, fz = (D[vec_in + c + '_fb_m' + str(m - 1)] for c in 'yz')
             elif M > 0:
@@ -315,32 +372,40 @@ class TransformerMethodsCL(GenericMethodsCL):
             else:
                 continue
             self.axpbyz(-1.j, fz, -1.0, fy, D['fld_buff0_c'])
-            self._dot(out, D['dDHT_minus_m' + str(m)], D['fld_buff0_c'], accumulate=True)
+            self._dot(out, own(D['dDHT_minus_m' + str(m)]), D['fld_buff0_c'], accumulate=True)
             if m < M:
                 fy, fz = (D[vec_in + c + '_fb_m' + str(m + 1)] for c in 'yz')
                 self.axpbyz(-1.j, fz, 1.0, fy, D['fld_buff0_c'])
-                self._dot(out, D['dDHT_plus_m' + str(m)], D['fld_buff0_c'], accumulate=True)
+                self._dot(out, own(D['dDHT_plus_m' + str(m)]), D['fld_buff0_c'],
+                          accumulate=True)
 
     def field_rot(self, fld_in, fld_out):
+        """Sharded solve: outputs and the element-wise sources are the owned rows; the
+        contraction sources fld_in{x,y,z}_fb_m* must be valid on ALL rows (all-gathered);
+        their linear combinations (fld_buff0_c) are formed on all rows by every shard."""
         D, M = self.DataDev, self.Args['M']
+        own = self._own
         fast0 = self._m0_pm_identical()
+        if self._shard_is_empty():
+            return
         if not fast0:
             self._get_mm1_vec(fld_in)
         for m in range(M + 1):
-            ox, oy, oz = (D[fld_out + c + '_fb_m' + str(m)] for c in 'xyz')
-            self.ab_dot_x(-1.j, D['kx'], D[fld_in + 'z' + '_fb_m' + str(m)], oy)
-            self.ab_dot_x(1.j, D['kx'], D[fld_in + 'y' + '_fb_m' + str(m)], oz)
+            ox, oy, oz = (own(D[fld_out + c + '_fb_m' + str(m)]) for c in 'xyz')
+            self.ab_dot_x(-1.j, D['kx'], own(D[fld_in + 'z' + '_fb_m' + str(m)]), oy)
+            self.ab_dot_x(1.j, D['kx'], own(D[fld_in + 'y' + '_fb_m' + str(m)]), oz)
             if m == 0 and fast0:
                 fx, fy, fz = (D[fld_in + c + '_fb_m1'] for c in 'xyz')
-                dp = D['dDHT_plus_m0']
+                dp = own(D['dDHT_plus_m0'])
+                b0, b1 = own(D['fld_buff0_c']), own(D['fld_buff1_c'])
                 # X+ = dDHT+.(fz + i fy); the m-1 term is conj(mirror(X+))
                 self.axpbyz(1, fz, 1.j, fy, D['fld_buff0_c'])
-                self._dot(D['fld_buff1_c'], dp, D['fld_buff0_c'])
-                self._mirror_axpy(ox, D['fld_buff1_c'], 1., 1., False)
+                self._dot(b1, dp, D['fld_buff0_c'])
+                self._mirror_axpy(ox, b1, 1., 1., False)
                 # b' = dDHT+.fx ; b = dDHT-.fx_{-1} = -conj(mirror(b'))
-                self._dot(D['fld_buff0_c'], dp, fx)
-                self._mirror_axpy(oy, D['fld_buff0_c'], -1.j, 1.j, True)   # oy -= i b + i b'
-                self._mirror_axpy(oz, D['fld_buff0_c'], -1., -1., True)    # oz += b - b'
+                self._dot(b0, dp, fx)
+                self._mirror_axpy(oy, b0, -1.j, 1.j, True)   # oy -= i b + i b'
+                self._mirror_axpy(oz, b0, -1., -1., True)    # oz += b - b'
                 continue
             if m > 0:
                 fx, fy, fz = (D[fld_in + c + '_fb_m' + str(m - 1)] for c in 'xyz')
@@ -349,14 +414,14 @@ class TransformerMethodsCL(GenericMethodsCL):
             else:
                 self.set_to(ox, 0.0)
                 continue
-            dm = D['dDHT_minus_m' + str(m)]
+            dm = own(D['dDHT_minus_m' + str(m)])
             self.axpbyz(-1, fz, 1.j, fy, D['fld_buff0_c'])
             self._dot(ox, dm, D['fld_buff0_c'])                       # ox  = dDHT-.(-fz + i fy)
             self._cdot2(dm, fx, oy, -1.j, True, oz, 1., True,         # oy -= i b, oz += b
                         hermitian=(m == 1 and self._m0_real()))
             if m < M:
                 fx, fy, fz = (D[fld_in + c + '_fb_m' + str(m + 1)] for c in 'xyz')
-                dp = D['dDHT_plus_m' + str(m)]
+                dp = own(D['dDHT_plus_m' + str(m)])
                 self.axpbyz(1, fz, 1.j, fy, D['fld_buff0_c'])
                 self._dot(ox, dp, D['fld_buff0_c'], accumulate=True)  # ox += dDHT+.(fz + i fy)
                 self._cdot2(dp, fx, oy, -1.j, True, oz, -1., True)    # oy -= i b, oz -= b

@@ -1,8 +1,11 @@
 """Multi-GPU plumbing: one process per GPU (torchrun), particles sharded over ranks,
-every rank holds the full grid; the only exchange step of the hot path is the sum
-of the raw rho / J deposits over ranks (NCCL all-reduce over NVLink), issued before
-the axis / volume post-processing.  The same code runs on gloo/CPU tensors for the
-world_size-2 tests."""
+every rank holds the full grid; the exchange step of the hot path is the sum of the raw
+rho / J deposits over ranks (NCCL all-reduce over NVLink), issued before the axis /
+volume post-processing.  With the kr-row sharded field solve (Solver.
+enable_spectral_sharding, opt-in) three more exchanges appear per step: the all-gather
+of the rho spectrum (for field_grad), the all-gather of the G spectra (for field_rot)
+and the sum of the partial backward contractions of E and B.  The same code runs on
+gloo/CPU tensors for the world_size-2 tests."""
 import os
 
 import torch
@@ -66,3 +69,58 @@ def allreduce_sum(tensors, group=None):
     for v in views:
         v.copy_(flat[off:off + v.numel()])
         off += v.numel()
+
+
+def spectral_rows(K, rank, world):
+    """kr rows [lo, hi) of the K = Nr-1 spectral rows owned by `rank`, and the chunk
+    height R all ranks share (a multiple of 8 -- operator-matrix slices stay 16-byte
+    aligned for the 128-bit operand loads of the contraction kernel; the last ranks may
+    own fewer than R rows, or none)."""
+    K, rank, world = int(K), int(rank), int(world)
+    R = (-(-K // world) + 7) // 8 * 8
+    lo = min(K, rank * R)
+    return lo, min(K, lo + R), R
+
+
+class _Works:
+    """Several async collectives waited for as one."""
+
+    def __init__(self, works):
+        self.works = [w for w in works if w is not None]
+
+    def wait(self):
+        for w in self.works:
+            w.wait()
+
+
+def allgather_rows_async(stores, rank, group=None):
+    """In-place all-gather of equally sized row chunks: every tensor of `stores` is a
+    contiguous (world*R, ...) array whose chunk [rank*R, (rank+1)*R) holds this rank's
+    rows; afterwards all chunks are valid on all ranks.  One collective per array, all in
+    flight together; returns one handle (None for a single rank)."""
+    if group is None and not dist.is_initialized():
+        return None
+    world = dist.get_world_size(group)
+    if world == 1:
+        return None
+    works = []
+    for st in stores:
+        flat = (torch.view_as_real(st) if st.is_complex() else st).reshape(-1)
+        n = flat.numel() // world
+        works.append(dist.all_gather_into_tensor(flat, flat[rank * n:(rank + 1) * n],
+                                                 group=group, async_op=True))
+    return _Works(works)
+
+
+def allreduce_each_async(tensors, group=None):
+    """Sum over ranks of every (contiguous) tensor in place, one async collective each;
+    returns one handle (None for a single rank)."""
+    if group is None and not dist.is_initialized():
+        return None
+    if dist.get_world_size(group) == 1:
+        return None
+    works = []
+    for t in tensors:
+        flat = (torch.view_as_real(t) if t.is_complex() else t).reshape(-1)
+        works.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=True))
+    return _Works(works)

@@ -91,6 +91,12 @@ class PIC_loop:
             hook(self)
 
         for solver in self.solvers:
+            if getattr(solver, 'spectral_sharding_enabled', lambda: False)():
+                self._deposit_and_solve_sharded(solver)
+                self.timer_start()
+                solver.gather_and_push(species=self.species)
+                self.timer_record('gather + push-p')
+                continue
             self.timer_start()
             multi = getattr(solver.comm, 'process_group', None) is not None and \
                 hasattr(solver, 'finish_charge')
@@ -160,6 +166,80 @@ class PIC_loop:
 
         self.it += 1
         return self.it
+
+    def _deposit_and_solve_sharded(self, solver):
+        """Charge deposit + field solve of one step with the kr-row sharded spectral solve
+        (Solver.enable_spectral_sharding): the same phases as in step(), each on the kr
+        rows this rank owns, plus the three exchanges the sharding needs.  What overlaps:
+        the J all-reduce with the charge deposits, the rho all-reduce with the forward
+        transform of J, the all-gather of G with the backward transform of E, and the
+        sum of the E partials with the B side (field_rot, backward transform of B)."""
+        self.timer_start()
+        solver.depose_charge(species=self.species, defer=True)
+        solver.finish_currents()
+        self.timer_record('depose')
+        self._solve_fields_sharded(solver, solver.finish_charge)
+
+    def _solve_fields_sharded(self, solver, charge_ready=None):
+        """From the deposited J (and, once charge_ready() has returned, rho) grids to the
+        E and B grids."""
+        S = solver.shards
+        self.timer_start()
+        for _ in S():
+            solver.fb_transform(vects=['J', ], dir=0, smooth=True)
+        if charge_ready is not None:
+            charge_ready()
+        for _ in S():
+            solver.fb_transform(scals=['rho', ], dir=0, smooth=True)
+        rho_ready = solver.gather_spectral(['rho'])
+        self.timer_record('transform')
+
+        self.timer_start()
+        for m in range(0, solver.Args['M'] + 1):
+            for comp in solver.Args['vec_comps']:
+                key = comp + '_fb_m' + str(m)
+                solver.DataDev['dN0' + key], solver.DataDev['dN1' + key] = \
+                    solver.DataDev['dN1' + key], solver.DataDev['dN0' + key]
+        self.timer_record('data_copy')
+
+        solver.m0_spectra_of_real_fields = self.real_m0_symmetry
+        self.timer_start()
+        rho_ready.wait()
+        for _ in S():
+            solver.field_grad('rho', 'dN1')
+        self.timer_record('grad')
+
+        self.timer_start()
+        for _ in S():
+            solver.push_fields()
+        self.timer_record('push-eb')
+
+        self.timer_start()
+        for _ in S():
+            solver.damp_fields()
+        g_ready = solver.gather_spectral(['G' + c for c in solver.Args['vec_comps']])
+        self.timer_record('damp-eb')
+
+        self.timer_start()
+        for _ in S():
+            solver.fb_transform(vects=['E'], dir=1)
+        e_ready = solver.reduce_grid_fields(['E'])
+        self.timer_record('transform')
+
+        self.timer_start()
+        g_ready.wait()
+        for _ in S():
+            solver.restore_B_fb()
+        self.timer_record('restore_B')
+        solver.m0_spectra_of_real_fields = False
+
+        self.timer_start()
+        for _ in S():
+            solver.fb_transform(vects=['B'], dir=1)
+        b_ready = solver.reduce_grid_fields(['B'])
+        e_ready.wait()
+        b_ready.wait()
+        self.timer_record('transform')
 
     def _can_fuse_first_half(self):
         for parts in self.species:

@@ -19,7 +19,108 @@ def psatd_coefficients(A):
     return A
 
 
-class Solver(Grid, Transformer, SolverMethodsCL):
+class _Shard:
+    """kr rows [lo, hi) one (real or virtual) rank owns; `first`: its partial backward
+    contractions overwrite the grid arrays (later virtual shards of a process add)."""
+    __slots__ = ("lo", "hi", "first")
+
+    def __init__(self, lo, hi, first=True):
+        self.lo, self.hi, self.first = int(lo), int(hi), bool(first)
+
+
+class _Done:
+    def wait(self):
+        pass
+
+
+class SpectralSharding:
+    """kr-row sharded field solve over the ranks of the Communicator's process group (no
+    reference counterpart: the reference is single-device).  Every rank keeps full-size
+    spectral arrays but only computes, and only keeps valid, the rows spectral_rows()
+    assigns to it: 1/world of the forward and backward contractions, FFTs, PSATD, damping
+    and grad / rot outputs.  Three exchanges per step make up for it, all on contiguous
+    row blocks (no packing): gather_spectral(['rho']) before field_grad,
+    gather_spectral(['Gx','Gy','Gz']) before field_rot (equal chunks of row-padded
+    storage, in-place all-gather), and reduce_grid_fields(['E']), (['B']) after the
+    backward transform, whose contraction over the owned kr rows leaves partial sums
+    (all-reduce of rows [1:] of every grid array).  PIC_loop.step() drives the sequence.
+
+    emulate=True runs all `world` shards one after the other in ONE process
+    (`for _ in solver.shards(): ...`): the single-GPU test of the row arithmetic."""
+
+    def enable_spectral_sharding(self, world=None, rank=None, emulate=False):
+        import torch
+        from .devarray import DevArray
+        from .parallel import spectral_rows
+        pg = getattr(self.comm, 'process_group', None)
+        if emulate:
+            world = int(world)
+        elif pg is not None:
+            import torch.distributed as dist
+            world, rank = dist.get_world_size(pg), dist.get_rank(pg)
+        else:
+            world, rank = 1, 0
+        K = int(self.Args['Nr']) - 1
+        R = spectral_rows(K, 0, world)[2]
+        self._sharding = {'world': world, 'rank': rank, 'emulate': bool(emulate), 'R': R,
+                          'stores': {}}
+        # all-gathered arrays live in storage of world*R >= K rows, so that the chunks
+        # are equal; DataDev keeps showing the (K, Nx) prefix under the same key
+        Nx = int(self.Args['Nx'])
+        for name in ['rho'] + ['G' + c for c in self.Args['vec_comps']]:
+            for m in range(self.Args['M'] + 1):
+                key = name + '_fb_m' + str(m)
+                store = torch.zeros((world * R, Nx), dtype=torch.complex128,
+                                    device=self.comm.device)
+                store[:K] = self.DataDev[key].t
+                self.DataDev[key] = DevArray(store[:K])
+                self._sharding['stores'][key] = store
+        self._shard = None if emulate else _Shard(*spectral_rows(K, rank, world)[:2])
+        return self
+
+    def spectral_sharding_enabled(self):
+        return self.__dict__.get('_sharding') is not None
+
+    def shards(self):
+        """Iterate over the shards this process computes: its own one (real ranks, or no
+        sharding at all), or all of them in turn (emulation)."""
+        from .parallel import spectral_rows
+        st = self.__dict__.get('_sharding')
+        if st is None or not st['emulate']:
+            yield st['rank'] if st is not None else 0
+            return
+        K = int(self.Args['Nr']) - 1
+        try:
+            for r in range(st['world']):
+                self._shard = _Shard(*spectral_rows(K, r, st['world'])[:2], first=(r == 0))
+                yield r
+        finally:
+            self._shard = None
+
+    def gather_spectral(self, names):
+        """Start the all-gather of the owned kr rows of names[i]_fb_m*; .wait() on the
+        result before the arrays are used as contraction sources."""
+        st = self.__dict__.get('_sharding')
+        if st is None or st['emulate'] or st['world'] == 1:
+            return _Done()
+        from .parallel import allgather_rows_async
+        stores = [st['stores'][n + '_fb_m' + str(m)] for n in names
+                  for m in range(self.Args['M'] + 1)]
+        return allgather_rows_async(stores, st['rank'], self.comm.process_group) or _Done()
+
+    def reduce_grid_fields(self, vects):
+        """Start the sum over ranks of the partial backward transforms of the vector
+        fields `vects` (rows [1:] of every component / mode); .wait() before use."""
+        st = self.__dict__.get('_sharding')
+        if st is None or st['emulate'] or st['world'] == 1:
+            return _Done()
+        from .parallel import allreduce_each_async
+        arrs = [self.DataDev[v + c + '_m' + str(m)].t[1:] for v in vects
+                for c in self.Args['vec_comps'] for m in range(self.Args['M'] + 1)]
+        return allreduce_each_async(arrs, self.comm.process_group) or _Done()
+
+
+class Solver(Grid, Transformer, SolverMethodsCL, SpectralSharding):
     def __init__(self, configs_in, comm):
         self.import_comm(comm)
         self._process_configs(configs_in)
