@@ -43,7 +43,8 @@ class SpectralSharding:
     gather_spectral(['Gx','Gy','Gz']) before field_rot (equal chunks of row-padded
     storage, in-place all-gather), and reduce_grid_fields(['E']), (['B']) after the
     backward transform, whose contraction over the owned kr rows leaves partial sums
-    (all-reduce of rows [1:] of every grid array).  PIC_loop.step() drives the sequence.
+    (one all-reduce per vector field, on a flat buffer holding its components and modes).
+    PIC_loop.step() drives the sequence.
 
     emulate=True runs all `world` shards one after the other in ONE process
     (`for _ in solver.shards(): ...`): the single-GPU test of the row arithmetic."""
@@ -75,6 +76,18 @@ class SpectralSharding:
                 store[:K] = self.DataDev[key].t
                 self.DataDev[key] = DevArray(store[:K])
                 self._sharding['stores'][key] = store
+        # E and B grids: one flat buffer per vector field (like J and rho), so that the sum
+        # of the partial backward transforms is ONE collective per field.  Row 0 of every
+        # array rides along; the backward transform never writes it and warp_axis
+        # overwrites it before the gather reads it.
+        shape = (int(self.Args['Nr']), Nx)
+        for v in ('E', 'B'):
+            names = [v + c for c in self.Args['vec_comps']]
+            old = {n + '_m' + str(m): self.DataDev[n + '_m' + str(m)].t
+                   for n in names for m in range(self.Args['M'] + 1)}
+            self._flat[v] = self._alloc_group(names, shape)
+            for key, t in old.items():
+                self.DataDev[key].t.copy_(t)
         self._shard = None if emulate else _Shard(*spectral_rows(K, rank, world)[:2])
         return self
 
@@ -110,14 +123,14 @@ class SpectralSharding:
 
     def reduce_grid_fields(self, vects):
         """Start the sum over ranks of the partial backward transforms of the vector
-        fields `vects` (rows [1:] of every component / mode); .wait() before use."""
+        fields `vects` (every component / mode, one collective per field); .wait()
+        before use."""
         st = self.__dict__.get('_sharding')
         if st is None or st['emulate'] or st['world'] == 1:
             return _Done()
         from .parallel import allreduce_each_async
-        arrs = [self.DataDev[v + c + '_m' + str(m)].t[1:] for v in vects
-                for c in self.Args['vec_comps'] for m in range(self.Args['M'] + 1)]
-        return allreduce_each_async(arrs, self.comm.process_group) or _Done()
+        return allreduce_each_async([self._flat[v] for v in vects],
+                                    self.comm.process_group) or _Done()
 
 
 class Solver(Grid, Transformer, SolverMethodsCL, SpectralSharding):
