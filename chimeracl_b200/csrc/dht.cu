@@ -39,6 +39,7 @@ struct GemmArgs {
   double* Cv[CHB_MAX_FIELDS];
   uint32_t lda, ldb, ldc;   // in doubles
   uint32_t M, N, K;         // N in doubles (2*Nx for complex data)
+  uint32_t ka;              // K rounded up to even: A columns the 16-byte loads may touch
   double alpha_re, alpha_im;
   int complex_pairs;        // columns are (re, im) pairs -> complex alpha allowed
   int accumulate;           // C += ... instead of C = ...
@@ -259,7 +260,10 @@ dht_gemm_wide_kernel(const __grid_constant__ GemmArgs p) {
     double* st = gemm_smem + stage * S::kStageDoubles;
 #pragma unroll
     for (int i = 0; i < kAPer; ++i) {
-      const bool ok = a_ok[i] && k0 + a_k[i] < p.lda;      // pad columns [K, lda) hold zeros
+      // column K of an odd-K operand is a (finite) pad or neighbour element of the same row
+      // and meets a zero-filled B row; nothing beyond it is touched, so A may be a column
+      // block of a larger matrix (the kr-sharded backward transform)
+      const bool ok = a_ok[i] && k0 + a_k[i] < p.ka;
       cp_async16_zfill(st + a_dst[i], ok ? a_src[i] : p.A, ok);
       a_src[i] += WBK;
     }
@@ -427,6 +431,7 @@ static int dht_launch(const double* A, uint32_t lda, const double* const* Bv, in
   p.ldb = is_complex ? 2 * ldb : ldb;
   p.ldc = is_complex ? 2 * ldc : ldc;
   p.M = M; p.K = K;
+  p.ka = (K + 1) & ~1u;
   p.N = is_complex ? 2 * N : N;
   p.alpha_re = alpha_re; p.alpha_im = alpha_im;
   p.complex_pairs = is_complex;
