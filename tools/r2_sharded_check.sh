@@ -1,0 +1,12 @@
+# First multi-GPU check of the kr-row sharded field solve; run on a
+# 2- or 8-GPU box:  gpurun --gpus N -- 'bash tools/r2_sharded_check.sh N'
+# Prints / stores the replicated and the sharded bench lines back to back.
+N=${1:-2}
+mkdir -p gpurun_out
+for flag in "" "--shard-spectral"; do
+  tag=replicated; [ -n "$flag" ] && tag=sharded
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 \
+    --master-port 29517 bench.py --gpus $N --steps 10 --warmup 3 --no-cpu-baseline $flag \
+    > gpurun_out/bench_${N}gpu_${tag}.json 2> gpurun_out/bench_${N}gpu_${tag}.err
+  tail -c 600 gpurun_out/bench_${N}gpu_${tag}.json
+done
