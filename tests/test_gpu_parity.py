@@ -763,17 +763,21 @@ def test_hermitian_contraction_matches_full(comm):
 
 
 # ----------------------------------------------------------------------------- kr-row sharded field solve
-@pytest.mark.parametrize("M,world", [(0, 2), (1, 2), (1, 3)])
+@pytest.mark.parametrize("M,world", [(0, 2), (1, 2), (1, 3), (1, 0)])
 def test_sharded_field_solve_virtual_shards_against_golden(comm, M, world):
     """Two full PIC steps with the field solve split into `world` kr-row shards run one
     after the other in this process (Solver.enable_spectral_sharding(emulate=True)):
     row-sliced operator matrices / FFT batches / PSATD ranges and the partial-sum
     backward transform must reproduce the golden run (K = 13: shards of 8 and 5 rows,
-    world = 3 has an empty shard)."""
+    world = 3 has an empty shard; world = 0: the non-emulated code path of a single rank,
+    which owns every row)."""
     from chimeracl_b200.pic_loop import PIC_loop
     G = load_golden(M)
     S, P, I = gpu_case_from_golden(G, comm)
-    S.enable_spectral_sharding(world=world, emulate=True)
+    if world:
+        S.enable_spectral_sharding(world=world, emulate=True)
+    else:
+        S.enable_spectral_sharding()
     loop = PIC_loop(solvers=[S], species=[P, I], frames=[], diags=[])
     loop.step()
     for k in G.files:

@@ -3,6 +3,8 @@
 # Prints / stores the replicated and the sharded bench lines back to back.
 N=${1:-2}
 mkdir -p gpurun_out
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 \
+  --master-port 29516 tools/sharded_parity.py 2>&1 | tail -3 | tee gpurun_out/sharded_parity_${N}gpu.txt
 for flag in "" "--shard-spectral"; do
   tag=replicated; [ -n "$flag" ] && tag=sharded
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 \
