@@ -202,31 +202,38 @@ __device__ __forceinline__ void cp_async_wait_group() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
-template <int NT>
+// WMW = warps along M: 8 -> 128-row tiles, 2 warps (16*NT columns) across; 4 -> 64-row
+// tiles, 4 warps (32*NT columns) across, for results of <= 64 rows (the owned kr rows of
+// a sharded forward / grad / rot contraction), which would fill half of a 128-row tile.
+// The warp tile (16 x 8*NT), and with it the fragment-load : DMMA ratio, is the same.
+template <int NT, int WMW = 8>
 struct WideShape {
-  static constexpr int kBN = 16 * NT;
+  static constexpr int kBM = 16 * WMW;
+  static constexpr int kWN = 16 / WMW;
+  static constexpr int kBN = kWN * 8 * NT;
   static constexpr int kLdb = kBN + 4;                 // (t*kLdb + g) mod 16 distinct (kBN % 16 == 0)
-  static constexpr int kStageDoubles = BM * WLDA + WBK * kLdb;
+  static constexpr int kStageDoubles = kBM * WLDA + WBK * kLdb;
   static constexpr int kSmem = kWideStages * kStageDoubles * (int)sizeof(double);
 };
 
-template <int NT>
+template <int NT, int WMW = 8>
 __global__ void __launch_bounds__(kWideThreads, 1)
 dht_gemm_wide_kernel(const __grid_constant__ GemmArgs p) {
-  using S = WideShape<NT>;
+  using S = WideShape<NT, WMW>;
   constexpr int BNW = S::kBN;
+  constexpr int BMW = S::kBM;
   extern __shared__ __align__(16) double gemm_smem[];
   const double* __restrict__ Bg = p.Bv[blockIdx.z];
   double* __restrict__ Cg = p.Cv[blockIdx.z];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
-  const int wm = warp >> 1, wn = warp & 1;          // wm: 0..7
-  const uint32_t m0 = blockIdx.y * BM, n0 = blockIdx.x * BNW;
+  const int wm = warp / S::kWN, wn = warp % S::kWN;  // wm: 0..WMW-1
+  const uint32_t m0 = blockIdx.y * BMW, n0 = blockIdx.x * BNW;
 
-  // cp.async assignment, fixed per thread for the whole k loop: the A slab is 128 rows x
+  // cp.async assignment, fixed per thread for the whole k loop: the A slab is BMW rows x
   // 16 chunks of 16 bytes, the B slab 32 rows x BNW/2 chunks; only the k offset moves
-  constexpr int kAPer = BM * (WBK / 2) / kWideThreads;                     // 4
+  constexpr int kAPer = BMW * (WBK / 2) / kWideThreads;                    // 4 (64 rows: 2)
   constexpr int kBChunks = WBK * (BNW / 2);
   constexpr int kBPer = (kBChunks + kWideThreads - 1) / kWideThreads;      // 4 (NT = 7: 3.5)
   const double* a_src[kAPer];
@@ -250,7 +257,7 @@ dht_gemm_wide_kernel(const __grid_constant__ GemmArgs p) {
     const int row = c / (BNW / 2), cc = (c - row * (BNW / 2)) * 2;
     b_ok[i] = c < kBChunks && n0 + cc < p.N;
     b_src[i] = Bg + (size_t)row * p.ldb + (b_ok[i] ? n0 + cc : 0);
-    b_dst[i] = BM * WLDA + row * S::kLdb + cc;
+    b_dst[i] = BMW * WLDA + row * S::kLdb + cc;
     b_k[i] = row;
   }
   const size_t b_step = (size_t)WBK * p.ldb;
@@ -294,7 +301,7 @@ dht_gemm_wide_kernel(const __grid_constant__ GemmArgs p) {
     cp_async_wait_group<kWideStages - 2>();   // slab `it` has landed (this thread's part)
     __syncthreads();                          // ... everybody's; slab it-1 fully consumed
     const double* As = gemm_smem + stage * S::kStageDoubles;
-    const double* Bs = As + BM * WLDA;
+    const double* Bs = As + BMW * WLDA;
 #pragma unroll
     for (int kk = 0; kk < WBK; kk += 4) {
       double a[2], b[NT];
@@ -349,19 +356,32 @@ dht_gemm_wide_kernel(const __grid_constant__ GemmArgs p) {
   }
 }
 
-template <int NT>
+template <int NT, int WMW = 8>
 static cudaError_t launch_wide(const GemmArgs& p, int nbatch, cudaStream_t st) {
-  using S = WideShape<NT>;
+  using S = WideShape<NT, WMW>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(dht_gemm_wide_kernel<NT>,
+    cudaError_t e = cudaFuncSetAttribute(dht_gemm_wide_kernel<NT, WMW>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, S::kSmem);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  dim3 grid((p.N + S::kBN - 1) / S::kBN, (p.M + BM - 1) / BM, nbatch);
-  dht_gemm_wide_kernel<NT><<<grid, kWideThreads, S::kSmem, st>>>(p);
+  dim3 grid((p.N + S::kBN - 1) / S::kBN, (p.M + S::kBM - 1) / S::kBM, nbatch);
+  dht_gemm_wide_kernel<NT, WMW><<<grid, kWideThreads, S::kSmem, st>>>(p);
   return cudaGetLastError();
+}
+
+// 64-row tiles: width 32*nt columns, nt = 4..7 (nt = 8 would not fit the shared memory)
+static int pick_wide64_nt(uint32_t N, int nbatch) {
+  int best = 0;
+  double best_cost = 0;
+  for (int nt = 4; nt <= 7; ++nt) {
+    const uint64_t tiles = (uint64_t)((N + 32 * nt - 1) / (32 * nt)) * nbatch;
+    const uint64_t waves = (tiles + kSMs - 1) / kSMs;
+    const double cost = (double)waves * nt;
+    if (best == 0 || cost <= best_cost) { best = nt; best_cost = cost; }
+  }
+  return best;
 }
 
 // tile width (in units of 16 columns) minimising waves x width on 148 SMs
@@ -457,6 +477,19 @@ static int dht_launch(const double* A, uint32_t lda, const double* const* Bv, in
   if (wide && hermitian && is_complex && N >= 4 && N % 2 == 0) {
     p.mirror_nx = N;                 // complex columns of the full result
     p.N = 2 * (N / 2 + 1);           // contracted: k = 0 .. Nx/2
+  }
+  // results of <= 64 rows (kr-sharded forward / grad / rot contractions): 64-row tiles.
+  // Opt-in (CHB_DHT_TILE64=1) until it has been validated and timed on a B200.
+  static const bool tile64 = [] { const char* e = getenv("CHB_DHT_TILE64"); return e && e[0] == '1'; }();
+  if (wide && tile64 && M <= 64) {
+    cudaError_t e;
+    switch (pick_wide64_nt(p.N, nbatch)) {
+      case 4: e = launch_wide<4, 4>(p, nbatch, (cudaStream_t)stream); break;
+      case 5: e = launch_wide<5, 4>(p, nbatch, (cudaStream_t)stream); break;
+      case 6: e = launch_wide<6, 4>(p, nbatch, (cudaStream_t)stream); break;
+      default: e = launch_wide<7, 4>(p, nbatch, (cudaStream_t)stream); break;
+    }
+    return e == cudaSuccess ? CHB_OK : (int)e;
   }
   if (wide) {
     cudaError_t e;

@@ -110,6 +110,7 @@ CASES = [
     (48, 30, 0, 2),      # Bluestein plan, M = 0
     (256, 42, 1, 4),     # K = 41, R = 16: [0,16) [16,32) [32,41) and an empty one
     (32, 19, 2, 2),
+    (32, 14, 1, 0),      # world 0: the non-emulated path of a single rank owning every row
 ]
 
 
@@ -129,7 +130,10 @@ def test_virtual_shards_equal_unsharded(Nx, Nr, M, world):
 
     S = make_solver(_cfg(Nx, Nr, M))
     _random_state(S, 7)
-    S.enable_spectral_sharding(world=world, emulate=True)
+    if world:
+        S.enable_spectral_sharding(world=world, emulate=True)
+    else:
+        S.enable_spectral_sharding()
     _Loop().solve_sharded(S)
     got = _results(S)
     for k in want:
