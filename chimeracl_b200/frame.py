@@ -37,6 +37,13 @@ class Frame():
             domain = {'Xmin': left, 'Xmax': left + x_shift,
                       'Rmin': grid.Args['Rmin'] * (grid.Args['Rmin'] > 0),
                       'Rmax': grid.Args['Rmax']}
+            # multi-GPU: the new slab is dealt to the ranks by bands of radial cell rows
+            # (equal particle counts; the deposits are summed over ranks anyway)
+            pg = getattr(getattr(specie, 'comm', None), 'process_group', None)
+            if pg is not None:
+                import torch.distributed as dist
+                if dist.get_world_size(pg) > 1:
+                    domain['r_shard'] = (dist.get_rank(pg), dist.get_world_size(pg))
             specie.make_new_domain(domain, density_profiles=self.Args['DensityProfiles'])
             if 'InjectorSource' in specie.Args.keys():
                 specie.add_new_particles(specie.Args['InjectorSource'])

@@ -104,6 +104,9 @@ class ParticleMethodsCL(GenericMethodsCL):
         self.flag_sorted = False
 
     def make_new_domain(self, parts_in, density_profiles=None):
+        """parts_in['r_shard'] = (rank, world) (optional, multi-GPU): only this rank's
+        contiguous band of the domain's radial cell rows is created -- every rank gets the
+        same number of particles per row, so the bands are balanced."""
         dev = self.comm.device
         xmin, xmax, rmin, rmax = [parts_in[k] for k in ('Xmin', 'Xmax', 'Rmin', 'Rmax')]
         dx, dr = self.Args['dx'], self.Args['dr']
@@ -112,6 +115,11 @@ class ParticleMethodsCL(GenericMethodsCL):
         Xgrid = xmin + dx * np.arange(Nx_loc)
         Rgrid = rmin + dr * np.arange(Nr_loc)
         self.Args['right_lim'] = Xgrid[-1]
+        if parts_in.get('r_shard') is not None:
+            from ..parallel import shard_range
+            j0, j1 = shard_range(Nr_loc - 1, *parts_in['r_shard'])
+            Rgrid = Rgrid[j0:j1 + 1]
+            Nr_loc = Rgrid.size
 
         npx, npr, npt = (int(v) for v in self.Args['Nppc'])
         ncx, ncr = Nx_loc - 1, Nr_loc - 1

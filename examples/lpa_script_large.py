@@ -74,8 +74,6 @@ def main():
             p.sort_parts(solver)
             p.align_parts()
     else:
-        if world > 1:
-            raise SystemExit("the moving-window injector is single-rank in this round")
         frames = [Frame({'Velocity': 1., 'dt': solver.Args['dt'], 'Steps': 20,
                          'DensityProfiles': dens_profiles})]
     if a.shard_spectral and world > 1:

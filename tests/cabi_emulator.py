@@ -207,6 +207,8 @@ class EmulatedComm:
         self.dev_type, self.plat_name = "CPU-emulated", "tests"
         self.process_group = process_group
         self.stream = None
+        self.generator = torch.Generator(device="cpu")
+        self.generator.manual_seed(99)
 
     def synchronize(self):
         pass

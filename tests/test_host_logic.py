@@ -134,3 +134,39 @@ def test_dht_tile_width_fills_whole_waves():
     assert -(-8192 // 112) * 4 == 296          # two full waves
     # the worst-case queue of the one-pass particle side: one 64-byte record per particle
     assert lib.chb_push_depose_workspace_bytes(1000) == 16 + 64 * 1000
+
+
+def test_injected_slab_is_dealt_to_ranks_by_radial_bands():
+    """Multi-GPU moving window: make_new_domain(..., r_shard=(rank, world)) creates one
+    band of radial cell rows per rank; the union of the bands is exactly the lattice a
+    single rank creates (x, r, weight; the per-cell theta offsets are random), with
+    equal particle counts per row (reference lattice: kernels/particles_generic.cl:33-84)."""
+    import torch
+    from cabi_emulator import EmulatedComm
+    from chimeracl_b200.particles import Particles
+
+    def make(shard):
+        P = Particles({'Nppc': (2, 2, 4), 'dx': 0.25, 'dr': 0.125, 'dt': 0.25, 'dens': 0.02,
+                       'charge': -1}, EmulatedComm())
+        dom = {'Xmin': 3.0, 'Xmax': 5.0, 'Rmin': 0.0, 'Rmax': 2.5, 'dpx': 0.01}
+        if shard is not None:
+            dom['r_shard'] = shard
+        P.make_new_domain(dom, density_profiles=[{'coord': 'x', 'points': [0, 3.5, 4.5, 9],
+                                                  'values': [0, 0, 1, 1]}])
+        D = P.DataDev
+        r = torch.sqrt(D['y_new'].t ** 2 + D['z_new'].t ** 2)
+        assert D['px_new'].size == D['x_new'].size == D['g_inv_new'].size
+        return D['x_new'].t.numpy(), r.numpy(), D['w_new'].t.numpy(), P.Args['right_lim']
+
+    x, r, w, lim = make(None)
+    world = 3
+    parts = [make((rank, world)) for rank in range(world)]
+    assert all(p[3] == lim for p in parts)
+    counts = [p[0].size for p in parts]
+    assert sum(counts) == x.size and max(counts) - min(counts) <= 9 * 16   # one cell row
+    xs, rs, ws = (np.concatenate([p[i] for p in parts]) for i in range(3))
+    key = lambda a, b: np.lexsort((np.round(b, 9), np.round(a, 9)))        # noqa: E731
+    i0, i1 = key(x, r), key(xs, rs)
+    assert np.array_equal(x[i0], xs[i1])
+    assert np.allclose(r[i0], rs[i1], rtol=1e-13, atol=1e-15)
+    assert np.allclose(w[i0], ws[i1], rtol=1e-13, atol=0)
