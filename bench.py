@@ -10,8 +10,10 @@ Metric: particle-steps/s = mobile particles x steps / time.
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 N > 1: launched by torchrun, one rank per GPU; every rank holds the full grid and its
-own 16 ppc shard of particles (weak scaling: per-GPU work fixed), rho/J are summed
-with NCCL every step.  --impl reference times the reference's own CPU implementation
+own 16 ppc shard of particles (weak scaling: per-GPU particle work fixed), rho/J are
+summed with NCCL every step, and the field solve on the (same-sized) grid is split over
+the ranks by kr rows (Solver.enable_spectral_sharding; --replicated-solve: every rank
+solves the whole grid, as in the single-GPU run).  --impl reference times the reference's own CPU implementation
 (oracle/_ref = chimeraCL's kernels host-compiled + OpenMP, np.dot, np.fft).
 """
 import argparse
@@ -266,10 +268,11 @@ def run_ours(args):
         p.sort_parts(solver)
         p.align_parts()
     np_gpu = int(eons.Args["Np"])
-    # opt-in (validated on CPU/gloo and by the virtual-shard GPU test; not yet timed on
-    # NVLink): kr-row sharded field solve instead of the replicated one
-    shard_solve = world > 1 and (args.shard_spectral or
-                                 os.environ.get("CHB_SHARD_SPECTRAL", "0") == "1")
+    # N > 1: kr-row sharded field solve (parity against the replicated
+    # solve 1.3e-14 over NCCL on 2 and 4 B200, 7.24 -> 6.17 and 7.40 -> 5.61 ms/step);
+    # --replicated-solve or CHB_SHARD_SPECTRAL=0 brings the replicated solve back
+    shard_solve = world > 1 and not args.replicated_solve and \
+        os.environ.get("CHB_SHARD_SPECTRAL", "1") != "0"
     if shard_solve:
         solver.enable_spectral_sharding()
     loop = PIC_loop(solvers=[solver], species=[eons, ions])
@@ -378,8 +381,10 @@ def run_ours(args):
         n_real, n_cplx = (10, 19) if Mm == 1 else ((10, 0) if Mm == 0 else (10, 35))
         # ... and the two contractions of m = 0 sources run on half of the kx columns
         n_cplx_exec = n_cplx - (3 if Mm >= 1 else 0) - (1 if Mm >= 1 and loop.real_m0_symmetry else 0)
-        flops = (0.5 * n_real + n_cplx) * flop_c
-        flops_exec = (0.5 * n_real + n_cplx_exec) * flop_c
+        # with the kr-row sharded solve a rank executes 1/world of every contraction
+        share = 1.0 / world if shard_solve else 1.0
+        flops = (0.5 * n_real + n_cplx) * flop_c * share
+        flops_exec = (0.5 * n_real + n_cplx_exec) * flop_c * share
         dht_ms = sum(kernels[k]["ms_per_step"] for k in dht_names)
         ach = flops / (dht_ms * 1e-3) / 1e12
         entry = {"bound": "tensor", "achieved": ach, "peak": dmma_tf, "unit": "TFLOP/s",
@@ -415,6 +420,8 @@ def run_ours(args):
             tr = json.load(f)
         for name, entry in rooflines.items():
             v = tr.get(ncu_kernel.get(name, ""), {}).get("dram_bytes_per_launch")
+            if shard_solve and name.startswith("chb_dht"):
+                v = None            # captured for the unsharded launch shapes
             if v:
                 entry["traffic"] = float(np.mean(v))
                 entry["traffic_source"] = "profiles/r1_ncu_traffic.json (ncu --set full, per launch)"
@@ -499,7 +506,9 @@ def main():
     ap.add_argument("--small", action="store_true", help="debug-size grid (not a bench config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--shard-spectral", action="store_true",
-                    help="N>1: kr-row sharded field solve (Solver.enable_spectral_sharding)")
+                    help="(default for N>1) kr-row sharded field solve")
+    ap.add_argument("--replicated-solve", action="store_true",
+                    help="N>1: every rank runs the whole field solve (the round-1 baseline)")
     args = ap.parse_args()
     if args.impl == "reference":
         if int(os.environ.get("RANK", "0")) != 0:

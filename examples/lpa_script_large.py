@@ -27,8 +27,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cfg5", action="store_true")
     ap.add_argument("--steps", type=int, default=60)
-    ap.add_argument("--shard-spectral", action="store_true",
-                    help="multi-GPU: kr-row sharded field solve instead of the replicated one")
+    ap.add_argument("--replicated-solve", action="store_true",
+                    help="multi-GPU: every rank runs the whole field solve (default: kr-row sharded)")
     a = ap.parse_args()
     comm = Communicator(answers=[0, 0])
     init_distributed(comm)
@@ -76,7 +76,7 @@ def main():
     else:
         frames = [Frame({'Velocity': 1., 'dt': solver.Args['dt'], 'Steps': 20,
                          'DensityProfiles': dens_profiles})]
-    if a.shard_spectral and world > 1:
+    if world > 1 and not a.replicated_solve:
         # after the laser initialiser: the spectra it wrote are complete on every rank
         solver.enable_spectral_sharding()
     loop = PIC_loop(solvers=[solver, ], species=[eons, ions], frames=frames, diags=[])

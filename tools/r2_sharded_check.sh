@@ -5,8 +5,8 @@ N=${1:-2}
 mkdir -p gpurun_out
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 \
   --master-port 29516 tools/sharded_parity.py 2>&1 | tail -3 | tee gpurun_out/sharded_parity_${N}gpu.txt
-for flag in "" "--shard-spectral"; do
-  tag=replicated; [ -n "$flag" ] && tag=sharded
+for flag in "--replicated-solve" ""; do
+  tag=replicated; [ -z "$flag" ] && tag=sharded
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 \
     --master-port 29517 bench.py --gpus $N --steps 10 --warmup 3 --no-cpu-baseline $flag \
     > gpurun_out/bench_${N}gpu_${tag}.json 2> gpurun_out/bench_${N}gpu_${tag}.err
@@ -17,6 +17,6 @@ done
 CHB_DHT_TILE64=1 timeout 600 python -m pytest tests/test_gpu_parity.py -q -k "sharded or dht_contraction or hermitian" \
   2>&1 | tail -3 | tee gpurun_out/tile64_pytest.txt
 CHB_DHT_TILE64=1 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 \
-  --master-port 29518 bench.py --gpus $N --steps 10 --warmup 3 --no-cpu-baseline --shard-spectral \
+  --master-port 29518 bench.py --gpus $N --steps 10 --warmup 3 --no-cpu-baseline \
   > gpurun_out/bench_${N}gpu_sharded_tile64.json 2> gpurun_out/bench_${N}gpu_sharded_tile64.err
 tail -c 600 gpurun_out/bench_${N}gpu_sharded_tile64.json
