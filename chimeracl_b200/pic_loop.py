@@ -214,10 +214,13 @@ class PIC_loop:
             solver.push_fields()
         self.timer_record('push-eb')
 
+        # G first: its all-gather then also runs under the damping of E
         self.timer_start()
         for _ in S():
-            solver.damp_fields()
+            solver.damp_fields(['G'])
         g_ready = solver.gather_spectral(['G' + c for c in solver.Args['vec_comps']])
+        for _ in S():
+            solver.damp_fields(['E'])
         self.timer_record('damp-eb')
 
         self.timer_start()

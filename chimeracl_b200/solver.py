@@ -150,12 +150,15 @@ class Solver(Grid, Transformer, SolverMethodsCL, SpectralSharding):
     def push_fields(self):
         self.advance_fields(vecs=['E', 'G', 'J', 'dN0', 'dN1'])
 
-    def damp_fields(self):
-        if self.damp_fields_fused(['E', 'G']):
+    def damp_fields(self, vects=('E', 'G')):
+        """Reference solver.py:32-35 (which always damps E and G); `vects` lets the sharded
+        step damp G ahead of E."""
+        vects = list(vects)
+        if self.damp_fields_fused(vects):
             return
-        self.fb_transform(vects=['E', 'G'], dir=1, mode='half')
-        self.profile_edges(['E', 'G'])
-        self.fb_transform(vects=['E', 'G'], dir=0, mode='half')
+        self.fb_transform(vects=vects, dir=1, mode='half')
+        self.profile_edges(vects)
+        self.fb_transform(vects=vects, dir=0, mode='half')
 
     def restore_B_fb(self):
         self.field_rot('G', 'B')

@@ -32,10 +32,6 @@ def _mat(ptr, rows, cols, ld, dtype):
     return np.lib.stride_tricks.as_strided(flat, (rows, cols), (ld * item, item))
 
 
-def _ptrs(arr, n):
-    return [arr[i] for i in range(int(n))]
-
-
 def _store(c, val, alpha, acc):
     val = alpha * val
     if acc:
@@ -50,7 +46,6 @@ class EmulatedLib:
 
     def __init__(self):
         self._real = real_lib.load()
-        self.calls = []
 
     def __getattr__(self, name):
         if name in ("chb_fft_max_pow2", "chb_version", "chb_error_string",
