@@ -12,12 +12,41 @@ import torch
 import torch.distributed as dist
 
 
+def bind_to_gpu_cpus(device):
+    """Pin the calling thread (and the threads it starts later) to the CPUs NVML reports as
+    local to `device`, so that host-side launches and, above all, the pinned staging buffers
+    of the host-buffer path (first touch) sit on the GPU's own NUMA node / PCIe root when
+    several ranks share a two-socket host.  Best effort: returns False (and changes nothing)
+    if NVML, the device or the CPU set is not available (e.g. a cpuset-restricted container);
+    CHB_NO_AFFINITY=1 disables it."""
+    if os.environ.get("CHB_NO_AFFINITY", "0") == "1":
+        return False
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        props = torch.cuda.get_device_properties(device)
+        try:
+            handle = pynvml.nvmlDeviceGetHandleByUUID("GPU-" + str(props.uuid))
+        except Exception:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(torch.device(device).index or 0)
+        before = os.sched_getaffinity(0)
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
+        if not os.sched_getaffinity(0):
+            os.sched_setaffinity(0, before)
+            return False
+        return True
+    except Exception:
+        return False
+
+
 def init_distributed(comm=None, backend=None):
     """Initialise torch.distributed from the torchrun environment (no-op for a
     single process) and attach the process group to the Communicator."""
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world <= 1:
         return None
+    if comm is not None and torch.cuda.is_available():
+        comm.cpu_affinity_bound = bind_to_gpu_cpus(comm.device)
     if not dist.is_initialized():
         if backend is None:
             backend = "nccl" if torch.cuda.is_available() else "gloo"

@@ -817,3 +817,17 @@ def test_sharded_field_solve_equals_replicated(comm, Nx, Nr, M, world):
         del S
     for k in outs[0]:
         assert rel_err(outs[1][k], outs[0][k]) < 1e-11, k
+
+
+def test_cpu_binding_is_best_effort(comm):
+    """parallel.bind_to_gpu_cpus (multi-rank runs: NUMA-local pinned buffers) never raises
+    and never leaves the process without CPUs."""
+    import os
+    from chimeracl_b200.parallel import bind_to_gpu_cpus
+    before = os.sched_getaffinity(0)
+    try:
+        ok = bind_to_gpu_cpus(comm.device)
+        assert ok in (True, False)
+        assert len(os.sched_getaffinity(0)) >= 1
+    finally:
+        os.sched_setaffinity(0, before)
