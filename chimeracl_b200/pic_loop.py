@@ -225,20 +225,20 @@ class PIC_loop:
 
         self.timer_start()
         for _ in S():
-            solver.fb_transform(vects=['E'], dir=1)
+            solver.fb_transform(vects=['E'], dir=1, partial=True)
         e_ready = solver.reduce_grid_fields(['E'])
         self.timer_record('transform')
 
         self.timer_start()
         g_ready.wait()
         for _ in S():
-            solver.restore_B_fb()
+            solver.restore_B_fb(gathered=True)
         self.timer_record('restore_B')
         solver.m0_spectra_of_real_fields = False
 
         self.timer_start()
         for _ in S():
-            solver.fb_transform(vects=['B'], dir=1)
+            solver.fb_transform(vects=['B'], dir=1, partial=True)
         b_ready = solver.reduce_grid_fields(['B'])
         e_ready.wait()
         b_ready.wait()

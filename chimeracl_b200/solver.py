@@ -160,7 +160,12 @@ class Solver(Grid, Transformer, SolverMethodsCL, SpectralSharding):
         self.profile_edges(vects)
         self.fb_transform(vects=vects, dir=0, mode='half')
 
-    def restore_B_fb(self):
+    def restore_B_fb(self, gathered=False):
+        """Reference solver.py:37-39.  On a kr-row sharded solver field_rot needs every kr
+        row of G: unless the caller has gathered them already (PIC_loop does, under the
+        backward transform of E), they are gathered here."""
+        if not gathered:
+            self.gather_spectral(['G' + c for c in self.Args['vec_comps']]).wait()
         self.field_rot('G', 'B')
         self.field_poiss_vec('B')
 

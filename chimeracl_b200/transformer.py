@@ -55,11 +55,26 @@ class Transformer(TransformerMethodsCL):
         self._make_spectral_axes()
         self._make_DHT()
 
-    def fb_transform(self, scals=[], vects=[], dir=0, mode='full', smooth=False):
+    def fb_transform(self, scals=[], vects=[], dir=0, mode='full', smooth=False, partial=False):
+        """Reference transformer.py:17-26.  On a kr-row sharded solver (Solver.
+        enable_spectral_sharding) the forward transform fills the owned spectral rows and
+        the full backward transform leaves this rank's partial sum in the grid arrays;
+        unless partial=True (PIC_loop overlaps the exchange itself) the partials are summed
+        over the ranks here, so a direct caller (Diagnostics, a user script) gets complete
+        grid fields."""
         comps = list(scals)
         for vect in vects:
             comps += [vect + comp for comp in self.Args['vec_comps']]
         self.transform_fields(comps, dir=dir, mode=mode, smooth=smooth)
+        if dir == 1 and mode == 'full' and not partial:
+            st = self.__dict__.get('_sharding')
+            if st is not None and not st['emulate'] and st['world'] > 1:
+                from .parallel import allreduce_each_async
+                work = allreduce_each_async(
+                    [self.DataDev[c + '_m' + str(m)].t[1:] for c in comps
+                     for m in range(self.Args['M'] + 1)], self.comm.process_group)
+                if work is not None:
+                    work.wait()
 
     def pad_operator_matrices(self):
         """Re-house the (Nr-1) x (Nr-1) DHT / dDHT matrices in storage with a leading

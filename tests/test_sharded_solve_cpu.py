@@ -182,6 +182,15 @@ def _worker(rank, world, port, out_dir, Nx, Nr, M):
     for step in range(2):
         _Loop().solve_sharded(S)
     res = _results(S)
+    # a direct caller (Diagnostics.add_field does this) gets complete grids from the
+    # backward transform: forward + backward of rho is the identity up to rounding
+    rho_before = [S.DataDev['rho_m%d' % m].get()[1:].copy() for m in range(M + 1)]
+    S.fb_transform(scals=['rho'], dir=0)
+    for m in range(M + 1):
+        S.DataDev['rho_m%d' % m].t[1:] = 0
+    S.fb_transform(scals=['rho'], dir=1)
+    for m in range(M + 1):
+        assert rel_err(S.DataDev['rho_m%d' % m].get()[1:], rho_before[m]) < 1e-9, m
     np.savez(os.path.join(out_dir, "rank%d.npz" % rank), lo=lo, hi=hi, **res)
     dist.barrier()
     dist.destroy_process_group()
