@@ -196,9 +196,9 @@ def _worker(rank, world, port, out_dir, Nx, Nr, M):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("Nx,Nr,M", [(32, 14, 1), (256, 26, 1)])
-def test_two_ranks_gloo_equal_unsharded(tmp_path, Nx, Nr, M):
-    world = 2
+@pytest.mark.parametrize("Nx,Nr,M,world", [(32, 14, 1, 2), (256, 26, 1, 2),
+                                           (32, 14, 1, 4)])    # K = 13: ranks 2, 3 own no rows
+def test_ranks_gloo_equal_unsharded(tmp_path, Nx, Nr, M, world):
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), Nx, Nr, M), nprocs=world,
              join=True)
     ref = make_solver(_cfg(Nx, Nr, M))
