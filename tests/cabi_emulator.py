@@ -1,7 +1,9 @@
-"""TEST INFRASTRUCTURE ONLY -- a NumPy stand-in for the spectral entry points of
-libchimera_b200.so, so that the HOST orchestration of the field solve (the transformer /
-solver mixins, the kr-row sharding and its collectives) can be exercised without a GPU:
-single process against the oracle, and world_size 2 over gloo.  Every function takes
+"""TEST INFRASTRUCTURE ONLY -- a NumPy stand-in for the entry points of
+libchimera_b200.so (spectral side: NumPy; particle side: the oracle's restatement of the
+reference kernels), so that the HOST orchestration (the mixins, PIC_loop's phase sequence
+including the one-pass particle side, the kr-row sharding and the collectives) can be
+exercised without a GPU: single process against the golden vectors, and several ranks
+over gloo.  Every function takes
 exactly the arguments of its C-ABI namesake in include/chimera_b200.h (raw addresses,
 sizes, scalars, stream) and works on host memory.  Nothing under chimeracl_b200/ imports
 this file; the product has no CPU path (Communicator raises without CUDA)."""
@@ -49,9 +51,150 @@ class EmulatedLib:
 
     def __getattr__(self, name):
         if name in ("chb_fft_max_pow2", "chb_version", "chb_error_string",
-                    "chb_dht_tile_columns"):
+                    "chb_dht_tile_columns", "chb_cell_offsets_workspace_bytes",
+                    "chb_sort_workspace_bytes", "chb_push_depose_workspace_bytes"):
             return getattr(self._real, name)
         raise AttributeError("cabi_emulator: %s is not emulated" % name)
+
+    # ---- particles and grid (oracle restatement of the reference kernels)
+    @staticmethod
+    def _geom(Nx, Nr, xmin, dx_inv, rmin, dr_inv):
+        return {"Nx": int(Nx), "Nr": int(Nr), "Xmin": float(_vec(xmin, 1, F8)[0]),
+                "dx_inv": float(_vec(dx_inv, 1, F8)[0]), "Rmin": float(_vec(rmin, 1, F8)[0]),
+                "dr_inv": float(_vec(dr_inv, 1, F8)[0]),
+                "Nxm1Nrm1": (int(Nx) - 1) * (int(Nr) - 1)}
+
+    @staticmethod
+    def _kern(M):
+        from oracle.np_kernels import NumpyKernels
+        return NumpyKernels(int(M))
+
+    def chb_push_xyz(self, x, y, z, px, py, pz, g_inv, dt, n, stream):
+        v = [_vec(p, n, F8) for p in (x, y, z, px, py, pz, g_inv)]
+        self._kern(0).push_xyz(*v, float(_vec(dt, 1, F8)[0]))
+        return 0
+
+    def chb_index_and_sum(self, x, y, z, indx, summ, n, Nx, Nr, xmin, dx_inv, rmin, dr_inv,
+                          stream):
+        g = self._geom(Nx, Nr, xmin, dx_inv, rmin, dr_inv)
+        i, s = self._kern(0).index_and_sum(_vec(x, n, F8), _vec(y, n, F8), _vec(z, n, F8), g)
+        _vec(indx, n, np.uint32)[...] = i
+        _vec(summ, g["Nxm1Nrm1"] + 1, np.uint32)[...] += s
+        return 0
+
+    def chb_push_index(self, x, y, z, px, py, pz, g_inv, dt, indx, summ, n, Nx, Nr, *geom_st):
+        self.chb_push_xyz(x, y, z, px, py, pz, g_inv, dt, n, None)
+        return self.chb_index_and_sum(x, y, z, indx, summ, n, Nx, Nr, *geom_st)
+
+    def chb_cell_offsets(self, summ, nbins, cell_offset, cursor, np_stay, ws, ws_bytes, stream):
+        s = _vec(summ, nbins, np.uint32)
+        off = _vec(cell_offset, nbins + 1, np.uint32)
+        off[0] = 0
+        off[1:] = np.cumsum(s, dtype=np.uint32)
+        if cursor:
+            _vec(cursor, nbins, np.uint32)[...] = off[:-1]
+        if np_stay:
+            _vec(np_stay, 1, np.uint32)[0] = off[nbins - 1]
+        return 0
+
+    def chb_sort_scatter_stable(self, indx, cell_offset, cursor, sort_indx, n, nbins, ws, wsb,
+                                stream):
+        out, _ = self._kern(0).sort_scatter(_vec(cell_offset, nbins + 1, np.uint32),
+                                            _vec(indx, n, np.uint32))
+        _vec(sort_indx, n, np.uint32)[...] = out
+        return 0
+
+    def chb_align(self, src, dst, nattr, sort_indx, np_stay, sort_out, stream):
+        s = _vec(sort_indx, np_stay, np.uint32).astype(np.int64)
+        hi = int(s.max()) + 1 if np_stay else 0
+        for k in range(nattr):
+            _vec(dst[k], np_stay, F8)[...] = _vec(src[k], hi, F8)[s]
+        if sort_out:
+            _vec(sort_out, np_stay, np.uint32)[...] = np.arange(np_stay, dtype=np.uint32)
+        return 0
+
+    def _mode_arrays(self, ptrs, count, M, per_mode, Nx, Nr):
+        out = []
+        for k in range(count):
+            m = k // per_mode
+            out.append(_vec(ptrs[k], Nx * Nr, C16 if m else F8).reshape(Nr, Nx))
+        return out
+
+    def chb_depose_scalar(self, M, sort_indx, x, y, z, w, cell_offset, charge, Nx, Nr, xmin,
+                          dx_inv, rmin, dr_inv, rho, stream, n=None):
+        g = self._geom(Nx, Nr, xmin, dx_inv, rmin, dr_inv)
+        off = _vec(cell_offset, g["Nxm1Nrm1"] + 2, np.uint32)
+        n = int(off[-1])
+        flds = self._mode_arrays(rho, M + 1, M, 1, Nx, Nr)
+        self._kern(M).depose_scalar(_vec(sort_indx, n, np.uint32), _vec(x, n, F8), _vec(y, n, F8),
+                                    _vec(z, n, F8), _vec(w, n, F8), off, charge, g, flds)
+        return 0
+
+    def chb_depose_vector(self, M, sort_indx, x, y, z, px, py, pz, g_inv, w, cell_offset, charge,
+                          Nx, Nr, xmin, dx_inv, rmin, dr_inv, j, stream):
+        g = self._geom(Nx, Nr, xmin, dx_inv, rmin, dr_inv)
+        off = _vec(cell_offset, g["Nxm1Nrm1"] + 2, np.uint32)
+        n = int(off[-1])
+        flds = self._mode_arrays(j, 3 * (M + 1), M, 3, Nx, Nr)
+        v = [_vec(p, n, F8) for p in (x, y, z, px, py, pz, g_inv, w)]
+        self._kern(M).depose_vector(_vec(sort_indx, n, np.uint32), *v, off, charge, g, flds)
+        return 0
+
+    def _push_depose(self, M, x, y, z, px, py, pz, g_inv, w, dt, n, charge, Nx, Nr, geom, j):
+        """push by dt, then the deposit a fresh sort at the new positions would give."""
+        K = self._kern(M)
+        g = self._geom(Nx, Nr, *geom)
+        v = [_vec(p, n, F8) for p in (x, y, z, px, py, pz, g_inv, w)]
+        K.push_xyz(*v[:7], float(_vec(dt, 1, F8)[0]))
+        indx, summ = K.index_and_sum(v[0], v[1], v[2], g)
+        off = np.concatenate(([0], np.cumsum(summ, dtype=np.uint32))).astype(np.uint32)
+        srt, _ = K.sort_scatter(off, indx)
+        K.depose_vector(srt, *v, off, charge, g, self._mode_arrays(j, 3 * (M + 1), M, 3, Nx, Nr))
+        return g, v
+
+    def chb_push_depose_vector(self, M, sort_indx, x, y, z, px, py, pz, g_inv, w, cell_offset,
+                               dt, n, charge, Nx, Nr, xmin, dx_inv, rmin, dr_inv, j, ws, wsb,
+                               stream):
+        self._push_depose(M, x, y, z, px, py, pz, g_inv, w, dt, n, charge, Nx, Nr,
+                          (xmin, dx_inv, rmin, dr_inv), j)
+        return 0
+
+    def chb_push_depose_push_index(self, M, sort_indx, x, y, z, px, py, pz, g_inv, w,
+                                   cell_offset, dt, n, charge, Nx, Nr, xmin, dx_inv, rmin,
+                                   dr_inv, j, indx, summ, ws, wsb, stream):
+        g, v = self._push_depose(M, x, y, z, px, py, pz, g_inv, w, dt, n, charge, Nx, Nr,
+                                 (xmin, dx_inv, rmin, dr_inv), j)
+        K = self._kern(M)
+        K.push_xyz(*v[:7], float(_vec(dt, 1, F8)[0]))
+        i, s = K.index_and_sum(v[0], v[1], v[2], g)
+        _vec(indx, n, np.uint32)[...] = i
+        _vec(summ, g["Nxm1Nrm1"] + 1, np.uint32)[...] += s
+        return 0
+
+    def chb_postproc_depose(self, flds, is_complex, nfld, Nx, Nr, dV_inv, stream):
+        dv = _vec(dV_inv, Nr, F8)
+        for k in range(nfld):
+            a = _vec(flds[k], Nx * Nr, C16 if is_complex[k] else F8).reshape(Nr, Nx)
+            a[1] -= a[0]
+            a *= dv[:, None]
+        return 0
+
+    def chb_warp_axis(self, flds, is_complex, nfld, Nx, stream):
+        for k in range(nfld):
+            a = _vec(flds[k], 2 * Nx, C16 if is_complex[k] else F8).reshape(2, Nx)
+            a[0] = -a[1] if is_complex[k] else a[1]
+        return 0
+
+    def chb_gather_push(self, M, x, y, z, px, py, pz, g_inv, sort_indx, cell_offset, factor, n,
+                        np_stay, Nx, Nr, xmin, dx_inv, rmin, dr_inv, eb, stream):
+        g = self._geom(Nx, Nr, xmin, dx_inv, rmin, dr_inv)
+        flds = self._mode_arrays(eb, 6 * (M + 1), M, 6, Nx, Nr)
+        v = [_vec(p, n, F8) for p in (x, y, z, px, py, pz, g_inv)]
+        self._kern(M).gather_and_push(*v, _vec(sort_indx, n, np.uint32),
+                                      _vec(cell_offset, g["Nxm1Nrm1"] + 2, np.uint32),
+                                      float(_vec(factor, 1, F8)[0]), n,
+                                      int(_vec(np_stay, 1, np.uint32)[0]), g, flds)
+        return 0
 
     # ---- element-wise
     def chb_mult_elementwise_d2c(self, x, z, n, stream):
@@ -211,13 +354,43 @@ class EmulatedComm:
     finish = synchronize
 
 
-def make_solver(cfg, process_group=None):
+def make_solver(cfg, process_group=None, comm=None):
     """A chimeracl_b200 Solver whose C-ABI calls land in EmulatedLib."""
     from chimeracl_b200.solver import Solver
-    comm = EmulatedComm(process_group)
+    comm = comm or EmulatedComm(process_group)
     saved = real_lib._lib
     real_lib._lib = comm.lib        # init_generic_methods() re-reads _lib.load()
     try:
         return Solver(dict(cfg), comm)
     finally:
         real_lib._lib = saved
+
+
+def make_particles(cfg, comm):
+    from chimeracl_b200.particles import Particles
+    saved = real_lib._lib
+    real_lib._lib = comm.lib
+    try:
+        return Particles(dict(cfg), comm)
+    finally:
+        real_lib._lib = saved
+
+
+class _HostEvent:
+    """torch.cuda.Event stand-in (the host code records one for the Np_stay read-back)."""
+
+    def __init__(self, *a, **k):
+        pass
+
+    def record(self, *a):
+        pass
+
+    def synchronize(self):
+        pass
+
+
+def patch_cuda_host_calls(monkeypatch):
+    """The particle mixin touches two CUDA-only host facilities (an event and pinned
+    memory for the asynchronous Np_stay read-back); give them host stand-ins."""
+    monkeypatch.setattr(torch.cuda, "Event", _HostEvent)
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
