@@ -151,3 +151,66 @@ def test_two_rank_pic_steps_equal_single_process(tmp_path, monkeypatch, sharded)
                 assert rel_err(got[k], P.DataDev[k[2:]].get()[lo:hi]) < 1e-10, (rank, k)
             else:
                 assert rel_err(got[k][1:], S.DataDev[k].get()[1:]) < 1e-10, (rank, k)
+
+
+# ------------------------------------------------------------------ moving window over ranks
+def _lwfa(comm, steps):
+    import importlib.util
+    from chimeracl_b200 import _lib as real_lib
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                        "examples", "lpa_script_small.py")
+    spec = importlib.util.spec_from_file_location("lpa_small", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    real_lib._lib = comm.lib                 # the wrapper classes bind _lib.load()
+    _, solver, eons, ions, frame, loop = mod.build(Nx=64, Nr=20, M=1, comm=comm)
+    for _ in range(steps):
+        loop.step()
+    # the plasma is neutral (ions sit on the electrons): look at the electron charge alone
+    solver.depose_charge(species=[eons])
+    return solver, eons, ions
+
+
+def _lwfa_worker(rank, world, port, out_dir, steps):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world))
+    torch.set_num_threads(1)
+    torch.cuda.Event = emu._HostEvent
+    torch.Tensor.pin_memory = lambda self, *a, **k: self
+    from chimeracl_b200.parallel import init_distributed
+    pg = init_distributed(backend="gloo")
+    solver, eons, ions = _lwfa(emu.EmulatedComm(pg), steps)
+    np.savez(os.path.join(out_dir, "lwfa%d.npz" % rank), rho=solver.DataDev["rho_m0"].get(),
+             ne=int(eons.Args["Np"]), ni=int(ions.Args["Np"]),
+             lim=float(eons.Args["right_lim"]), xmin=float(solver.Args["Xmin"]),
+             r_max=float(np.hypot(eons.DataDev["y"].get(), eons.DataDev["z"].get()).max()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_moving_window_injection_over_two_ranks(tmp_path, monkeypatch):
+    """examples/lpa_script_small.py (reduced grid) for 21 steps = two injections, on two
+    gloo ranks: every new slab is dealt to the ranks by radial bands (Frame.inject_plasma ->
+    make_new_domain(r_shard=...)).  Particle counts add up to the single-process run, both
+    ranks keep the same right_lim / window position, rank 0 holds the inner band, and the
+    summed m = 0 electron charge equals the single-process one (it does not depend on the random
+    per-cell theta offsets, and the new plasma has barely moved)."""
+    from chimeracl_b200 import _lib as real_lib
+    world, steps = 2, 21
+    mp.spawn(_lwfa_worker, args=(world, _free_port(), str(tmp_path), steps), nprocs=world,
+             join=True)
+    emu.patch_cuda_host_calls(monkeypatch)
+    monkeypatch.setattr(real_lib, "_lib", real_lib._lib)      # restored after the test
+    solver, eons, ions = _lwfa(emu.EmulatedComm(), steps)
+    got = [np.load(tmp_path / ("lwfa%d.npz" % r)) for r in range(world)]
+    assert sum(int(g["ne"]) for g in got) == int(eons.Args["Np"]) > 0
+    assert sum(int(g["ni"]) for g in got) == int(ions.Args["Np"])
+    assert abs(int(got[0]["ne"]) - int(got[1]["ne"])) <= 2 * 21 * 16      # one cell row
+    for g in got:
+        assert abs(float(g["lim"]) - float(eons.Args["right_lim"])) < 1e-9
+        assert abs(float(g["xmin"]) - float(solver.Args["Xmin"])) < 1e-12
+    assert float(got[0]["r_max"]) < float(got[1]["r_max"])
+    rho = solver.DataDev["rho_m0"].get()
+    assert np.abs(rho).max() > 0
+    for g in got:                                   # rho is all-reduced: complete on both
+        assert rel_err(g["rho"][1:], rho[1:]) < 1e-6
