@@ -2,7 +2,7 @@
 every rank holds the full grid; the exchange step of the hot path is the sum of the raw
 rho / J deposits over ranks (NCCL all-reduce over NVLink), issued before the axis /
 volume post-processing.  With the kr-row sharded field solve (Solver.
-enable_spectral_sharding, opt-in) three more exchanges appear per step: the all-gather
+enable_spectral_sharding; what bench.py uses for N > 1) three more exchanges appear per step: the all-gather
 of the rho spectrum (for field_grad), the all-gather of the G spectra (for field_rot)
 and the sum of the partial backward contractions of E and B.  The same code runs on
 gloo/CPU tensors for the world_size-2 tests."""

@@ -3,7 +3,9 @@
 The step sequence is the reference's (pic_loop.py:57-142); every phase only enqueues
 work on the rank's CUDA stream -- there is no host synchronisation inside a step.
 With timit=True the phases are bracketed by CUDA events and accumulated (in seconds)
-under the reference's Timer keys."""
+under the reference's Timer keys.  A solver with a kr-row sharded field solve
+(Solver.enable_spectral_sharding, multi-GPU) takes _deposit_and_solve_sharded: the same
+phases on the owned rows plus the exchanges the sharding needs."""
 import numpy as np
 import torch
 
