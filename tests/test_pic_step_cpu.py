@@ -214,3 +214,31 @@ def test_moving_window_injection_over_two_ranks(tmp_path, monkeypatch):
     assert np.abs(rho).max() > 0
     for g in got:                                   # rho is all-reduced: complete on both
         assert rel_err(g["rho"][1:], rho[1:]) < 1e-6
+
+
+# ------------------------------------------------------------------ laser initialiser
+@pytest.mark.parametrize("M", [0, 1])
+def test_laser_initialiser_matches_oracle(M):
+    """chimeracl_b200.laser.add_gausian_pulse (reference laser.py:3-37: host NumPy math
+    around fb_transform / restore_B_fb) through the real Solver mixins on the emulated
+    C ABI, against the oracle's restatement."""
+    from oracle import orchestration as O
+    from oracle.np_kernels import NumpyKernels
+    from chimeracl_b200.laser import add_gausian_pulse
+    cfg = {'Xmin': -20.0, 'Xmax': 20.0, 'Nx': 128, 'Rmin': 0.0, 'Rmax': 12.0, 'Nr': 24, 'M': M,
+           'DampCells': 10}
+    cfg['dt'] = (cfg['Xmax'] - cfg['Xmin']) / cfg['Nx']
+    laser = {'k0': 1., 'a0': 2.0, 'x0': 2.0, 'Lx': 4.0, 'R': 3.0, 'x_foc': 15.0}
+    S = emu.make_solver(cfg)
+    add_gausian_pulse(S, dict(laser))
+    So = O.OracleSolver(dict(cfg), NumpyKernels(M))
+    O.add_gaussian_pulse(So, dict(laser))
+    assert np.abs(So.D['Ez_m0']).max() > 0.5
+    for k in ('Ez_fb_m0', 'Gz_fb_m0', 'Bx_fb_m0', 'By_fb_m0'):
+        assert rel_err(S.DataDev[k].get(), So.D[k]) < 1e-11, k
+    for f in 'EB':
+        for c in 'xyz':
+            k = '%s%s_m0' % (f, c)
+            ref = So.D[k][1:]
+            scale = max(np.abs(So.D['Ez_m0']).max(), 1e-300)
+            assert np.abs(S.DataDev[k].get()[1:] - ref).max() / scale < 1e-11, k
