@@ -1,22 +1,33 @@
-# First multi-GPU check of the kr-row sharded field solve; run on a
-# 2- or 8-GPU box:  gpurun --gpus N -- 'bash tools/r2_sharded_check.sh N'
-# Prints / stores the replicated and the sharded bench lines back to back.
-N=${1:-2}
+# Multi-GPU check list for the kr-row sharded field solve; run on an
+# N-GPU box:   gpurun --gpus N --timeout 900 -- 'bash tools/r2_sharded_check.sh N'
+# (round 1 covered N = 2 and 4; N = 8 and cfg5 are open).  Everything lands in gpurun_out/.
+N=${1:-8}
 mkdir -p gpurun_out
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 \
-  --master-port 29516 tools/sharded_parity.py 2>&1 | tail -3 | tee gpurun_out/sharded_parity_${N}gpu.txt
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
+
+# 1. parity: three PIC steps, sharded against replicated, on every rank
+timeout 300 $TR --master-port 29516 tools/sharded_parity.py 2>&1 | tail -2 | tee gpurun_out/sharded_parity_${N}gpu.txt
+
+# 2. bench: replicated, sharded, sharded with the collectives on a high-priority stream
+#    (the contraction kernel holds whole SMs, NCCL only gets them between waves)
+bench() {  # tag, env, extra flags
+  env $2 timeout 300 $TR --master-port 29517 bench.py --gpus $N --steps 10 --warmup 3 --no-cpu-baseline $3 \
+    > gpurun_out/bench_${N}gpu_$1.json 2> gpurun_out/bench_${N}gpu_$1.err
+  python - "$1" <<PY
+import json, sys
+d = json.load(open("gpurun_out/bench_${N}gpu_%s.json" % sys.argv[1]))
+print("%-22s %.3f ms/step  %.3g particle-steps/s  e2e %.1f ms/step" %
+      (sys.argv[1], d["ms_per_step"], d["value"], d["e2e"]["ms_per_step"]))
+print("   phases", {k: round(v, 3) for k, v in d["phases_ms"].items() if v > 0.05})
+PY
+}
+bench replicated "A=0" "--replicated-solve"
+bench sharded "A=0" ""
+bench sharded_hiprio "TORCH_NCCL_HIGH_PRIORITY=1" ""
+bench sharded_tile64 "CHB_DHT_TILE64=1" ""
+
+# 3. cfg5 (Nx=16384, Nr=1024, M=2, 32 ppc): replicated against sharded solve
 for flag in "--replicated-solve" ""; do
-  tag=replicated; [ -z "$flag" ] && tag=sharded
-  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 \
-    --master-port 29517 bench.py --gpus $N --steps 10 --warmup 3 --no-cpu-baseline $flag \
-    > gpurun_out/bench_${N}gpu_${tag}.json 2> gpurun_out/bench_${N}gpu_${tag}.err
-  tail -c 600 gpurun_out/bench_${N}gpu_${tag}.json
+  timeout 600 $TR --master-port 29518 examples/lpa_script_large.py --cfg5 --steps 10 $flag 2>&1 \
+    | grep "ms/step" | tee -a gpurun_out/cfg5_${N}gpu.txt
 done
-# 64-row contraction tiles for the owned-row outputs (opt-in until validated): parity on one
-# GPU with the virtual-shard tests, then the sharded bench again
-CHB_DHT_TILE64=1 timeout 600 python -m pytest tests/test_gpu_parity.py -q -k "sharded or dht_contraction or hermitian" \
-  2>&1 | tail -3 | tee gpurun_out/tile64_pytest.txt
-CHB_DHT_TILE64=1 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 \
-  --master-port 29518 bench.py --gpus $N --steps 10 --warmup 3 --no-cpu-baseline \
-  > gpurun_out/bench_${N}gpu_sharded_tile64.json 2> gpurun_out/bench_${N}gpu_sharded_tile64.err
-tail -c 600 gpurun_out/bench_${N}gpu_sharded_tile64.json
