@@ -478,10 +478,13 @@ static int dht_launch(const double* A, uint32_t lda, const double* const* Bv, in
     p.mirror_nx = N;                 // complex columns of the full result
     p.N = 2 * (N / 2 + 1);           // contracted: k = 0 .. Nx/2
   }
-  // results of <= 64 rows (kr-sharded forward / grad / rot contractions): 64-row tiles.
-  // Opt-in (CHB_DHT_TILE64=1) until it has been validated and timed on a B200.
-  static const bool tile64 = [] { const char* e = getenv("CHB_DHT_TILE64"); return e && e[0] == '1'; }();
-  if (wide && tile64 && M <= 64) {
+  // results of <= 64 rows (kr-sharded forward / grad / rot contractions at 8 ranks): 64-row
+  // tiles.  Measured with the 8 shards of cfg3 on one B200 (profiles/r1h_tile64_timing.txt):
+  // batched launches 19 % faster, single right-hand sides 5-25 % slower (too few tiles), so
+  // the default takes them for >= 3 right-hand sides; CHB_DHT_TILE64=0 / 1: never / always.
+  static const int tile64 = [] { const char* e = getenv("CHB_DHT_TILE64");
+                                 return e ? (e[0] == '1' ? 1 : 0) : 2; }();
+  if (wide && M <= 64 && (tile64 == 1 || (tile64 == 2 && nbatch >= 3))) {
     cudaError_t e;
     switch (pick_wide64_nt(p.N, nbatch)) {
       case 4: e = launch_wide<4, 4>(p, nbatch, (cudaStream_t)stream); break;

@@ -43,6 +43,6 @@ for _ in range(n):
     run()
 rep = lib.profile_report()
 lib.disable_profiling()
-print("tile64=%s world=%d: %.3f ms per solve (all shards)" % (os.environ.get("CHB_DHT_TILE64", "0"), world, total))
+print("tile64=%s world=%d: %.3f ms per solve (all shards)" % (os.environ.get("CHB_DHT_TILE64", "auto"), world, total))
 for k, (c, t) in sorted(rep.items(), key=lambda kv: -kv[1][1]):
     print("  %-28s %5.1f calls  %.3f ms" % (k, c / n, t / n))

@@ -24,7 +24,7 @@ PY
 bench replicated "A=0" "--replicated-solve"
 bench sharded "A=0" ""
 bench sharded_hiprio "TORCH_NCCL_HIGH_PRIORITY=1" ""
-bench sharded_tile64 "CHB_DHT_TILE64=1" ""
+bench sharded_tile128 "CHB_DHT_TILE64=0" ""
 
 # 3. cfg5 (Nx=16384, Nr=1024, M=2, 32 ppc): replicated against sharded solve
 for flag in "--replicated-solve" ""; do
