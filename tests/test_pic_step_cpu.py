@@ -242,3 +242,17 @@ def test_laser_initialiser_matches_oracle(M):
             ref = So.D[k][1:]
             scale = max(np.abs(So.D['Ez_m0']).max(), 1e-300)
             assert np.abs(S.DataDev[k].get()[1:] - ref).max() / scale < 1e-11, k
+
+
+# ------------------------------------------------------------------ diagnostics hook
+def test_diagnostics_records_host_side(tmp_path, monkeypatch):
+    """The checks of tests/test_gpu_parity.py::test_diagnostics_records (record layout of
+    reference diagnostics.py:57-141, selections, weight scaling, the re-deposit / transform
+    sequence of add_field) with the C ABI emulated: the Diagnostics class and the calls
+    it makes into the solver are host logic."""
+    from chimeracl_b200 import _lib as real_lib
+    from test_gpu_parity import test_diagnostics_records as body
+    emu.patch_cuda_host_calls(monkeypatch)
+    comm = emu.EmulatedComm()
+    monkeypatch.setattr(real_lib, "_lib", comm.lib)
+    body(comm, tmp_path, monkeypatch)
