@@ -157,12 +157,29 @@ class TransformerMethodsCL(GenericMethodsCL):
         """Rows of a (Nr-1, ...) spectral array / filter / operator matrix owned by the
         current shard (the array itself when the solve is not sharded)."""
         sh = self.__dict__.get('_shard')
-        return a if sh is None else a[sh.lo:sh.hi]
+        if sh is None:
+            return a
+        # the views are cached (keyed by storage address and extent, so that a fresh
+        # `arr[1:]` view of the same storage hits too): ~170 slices per step otherwise
+        cache = self.__dict__.setdefault('_own_cache', {})
+        t = a.t
+        key = (t.data_ptr(), t.dtype, t.shape, t.stride(0), sh.lo, sh.hi)
+        view = cache.get(key)
+        if view is None:
+            view = cache[key] = a[sh.lo:sh.hi]
+        return view
 
     def _kcols(self, mat):
         """Operator columns matching the owned rows of a right-hand side."""
         sh = self.__dict__.get('_shard')
-        return mat if sh is None else mat[:, sh.lo:sh.hi]
+        if sh is None:
+            return mat
+        cache = self.__dict__.setdefault('_own_cache', {})
+        key = (mat.t.data_ptr(), 'cols', sh.lo, sh.hi)
+        view = cache.get(key)
+        if view is None:
+            view = cache[key] = mat[:, sh.lo:sh.hi]
+        return view
 
     def _shard_is_empty(self):
         sh = self.__dict__.get('_shard')
