@@ -28,6 +28,7 @@ SOURCES = {
     "spectral.cu": [],
     "dht.cu": [],
     "fft.cu": [],
+    "peer.cu": [],
 }
 
 

@@ -1,0 +1,90 @@
+// chimera-b200: sum of the ranks' partial backward transforms over NVLink peer memory.
+//
+// The kr-row sharded field solve leaves, on every rank, a partial
+// sum of the E (or B) grid arrays in one flat FP64 buffer.  With those buffers allocated
+// as symmetric memory (torch.distributed._symmetric_memory: every rank knows every rank's
+// buffer address, and on NVSwitch a multicast address that maps all of them) the sum is
+// ONE kernel per field instead of an NCCL all-reduce: rank r owns the r-th 1/world block
+// of the buffer, reads that block from every rank, adds, and stores the total back into
+// every rank's buffer --
+//   * peer mode:      `world` 16-byte loads and `world` 16-byte stores per element pair
+//                     through the peers' addresses (P2P over NVLink),
+//   * multicast mode: one multimem.ld_reduce (the switch adds the `world` copies) and one
+//                     multimem.st (the switch fans the result out) per element.
+// The caller brackets the launch with two cross-rank barriers on the same stream (all
+// partials written / all totals stored): the symmetric-memory handle's barrier().
+// No reference counterpart (the reference is single-device).
+//
+// STATUS: compiled for sm_100a, not yet run on hardware (added when the round's GPU budget
+// was spent); reachable only with CHB_PEER_EXCHANGE=1 / multimem.
+#include "common.cuh"
+#include "../../include/chimera_b200.h"
+
+namespace chb {
+
+constexpr int kMaxPeers = 16;
+
+struct PeerBufs {
+  double* p[kMaxPeers];
+};
+
+// block [begin, end) of this rank, in doubles; begin/end even (16-byte aligned pairs)
+__global__ void __launch_bounds__(512)
+peer_allreduce_kernel(const __grid_constant__ PeerBufs bufs, int world, size_t begin, size_t end) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x * 2;
+  for (size_t i = begin + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2; i < end;
+       i += stride) {
+    double2 v[kMaxPeers];
+#pragma unroll
+    for (int r = 0; r < kMaxPeers; ++r)
+      if (r < world) v[r] = __ldcg(reinterpret_cast<const double2*>(bufs.p[r] + i));
+    double2 s = v[0];
+#pragma unroll
+    for (int r = 1; r < kMaxPeers; ++r)
+      if (r < world) { s.x += v[r].x; s.y += v[r].y; }      // rank order: same bits everywhere
+#pragma unroll
+    for (int r = 0; r < kMaxPeers; ++r)
+      if (r < world) *reinterpret_cast<double2*>(bufs.p[r] + i) = s;
+  }
+}
+
+__global__ void __launch_bounds__(512)
+multimem_allreduce_kernel(double* mc, size_t begin, size_t end) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < end; i += stride) {
+    double v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f64 %0, [%1];"
+                 : "=d"(v) : "l"(mc + i) : "memory");
+    asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(mc + i), "d"(v) : "memory");
+  }
+}
+
+}  // namespace chb
+
+using namespace chb;
+
+extern "C" int chb_peer_allreduce_f64(const uint64_t* peer_ptrs_host, int world, int rank,
+                                      uint64_t multicast_ptr, size_t n, void* stream) {
+  if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world || !peer_ptrs_host)
+    return CHB_ERR_ARG;
+  if (n == 0 || world == 1) return CHB_OK;
+  // equal blocks of an even number of doubles; the last rank takes the remainder
+  size_t per = (n / world) & ~(size_t)1;
+  const size_t begin = per * rank;
+  const size_t end = rank == world - 1 ? n : begin + per;
+  if (end <= begin) return CHB_OK;
+  const int grid = 4 * kSMs;
+  if (multicast_ptr) {
+    multimem_allreduce_kernel<<<grid, 512, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<double*>(multicast_ptr), begin, end);
+    CHB_RETURN_LAST_ERROR();
+  }
+  if ((n & 1) || (end & 1)) return CHB_ERR_ARG;     // pairs: the flat buffers are even-sized
+  PeerBufs bufs;
+  for (int r = 0; r < kMaxPeers; ++r) {
+    bufs.p[r] = r < world ? reinterpret_cast<double*>(peer_ptrs_host[r]) : nullptr;
+    if (r < world && (peer_ptrs_host[r] & 15)) return CHB_ERR_ARG;
+  }
+  peer_allreduce_kernel<<<grid, 512, 0, (cudaStream_t)stream>>>(bufs, world, begin, end);
+  CHB_RETURN_LAST_ERROR();
+}

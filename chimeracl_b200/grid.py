@@ -126,7 +126,9 @@ class Grid(GridMethodsCL):
         for group, names in (('J', ['J' + comp for comp in comps]), ('rho', ['rho'])):
             self._flat[group] = self._alloc_group(names, shape)
 
-    def _alloc_group(self, names, shape):
+    def _alloc_group(self, names, shape, alloc=None):
+        """alloc(n) -> zeroed flat float64 device tensor of n elements (default: torch.zeros;
+        the peer-memory exchange passes a symmetric-memory allocator)."""
         import torch
         from .devarray import DevArray
         n = shape[0] * shape[1]
@@ -135,8 +137,9 @@ class Grid(GridMethodsCL):
         for name in names:
             for m in range(self.Args['M'] + 1):
                 sizes.append((name + '_m' + str(m), n_pad if m == 0 else 2 * n_pad, m > 0))
-        flat = torch.zeros(sum(sz for _, sz, _ in sizes), dtype=torch.float64,
-                           device=self.comm.device)
+        total = sum(sz for _, sz, _ in sizes)
+        flat = alloc(total) if alloc is not None else \
+            torch.zeros(total, dtype=torch.float64, device=self.comm.device)
         off = 0
         for key, sz, cplx in sizes:
             if cplx:

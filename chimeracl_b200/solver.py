@@ -81,13 +81,29 @@ class SpectralSharding:
         # array rides along; the backward transform never writes it and warp_axis
         # overwrites it before the gather reads it.
         shape = (int(self.Args['Nr']), Nx)
+        # CHB_PEER_EXCHANGE=1 | multimem (opt-in, not yet run on hardware): the flat buffers
+        # are symmetric memory and the sum is chb_peer_allreduce_f64 (P2P loads / stores or
+        # NVSwitch multimem) between two cross-rank barriers instead of an NCCL all-reduce
+        import os
+        peer = os.environ.get('CHB_PEER_EXCHANGE', '0')
+        alloc = None
+        if peer != '0' and not emulate and world > 1:
+            import torch.distributed._symmetric_memory as symm
+            alloc = lambda n: symm.empty(n, dtype=torch.float64, device=self.comm.device).zero_()  # noqa: E731
+            self._sharding['peer'] = {}
         for v in ('E', 'B'):
             names = [v + c for c in self.Args['vec_comps']]
             old = {n + '_m' + str(m): self.DataDev[n + '_m' + str(m)].t
                    for n in names for m in range(self.Args['M'] + 1)}
-            self._flat[v] = self._alloc_group(names, shape)
+            self._flat[v] = self._alloc_group(names, shape, alloc)
             for key, t in old.items():
                 self.DataDev[key].t.copy_(t)
+            if alloc is not None:
+                import ctypes
+                hdl = symm.rendezvous(self._flat[v], group=pg)
+                ptrs = [int(p) for p in hdl.buffer_ptrs]
+                mc = int(getattr(hdl, 'multicast_ptr', 0) or 0) if peer == 'multimem' else 0
+                self._sharding['peer'][v] = (hdl, (ctypes.c_uint64 * world)(*ptrs), mc)
         self._shard = None if emulate else _Shard(*spectral_rows(K, rank, world)[:2])
         return self
 
@@ -127,6 +143,14 @@ class SpectralSharding:
         before use."""
         st = self.__dict__.get('_sharding')
         if st is None or st['emulate'] or st['world'] == 1:
+            return _Done()
+        if 'peer' in st:
+            for v in vects:
+                hdl, ptrs, mc = st['peer'][v]
+                hdl.barrier(channel=0)             # every rank's partial sums are written
+                self._call('chb_peer_allreduce_f64', ptrs, st['world'], st['rank'], mc,
+                           self._flat[v].numel())
+                hdl.barrier(channel=1)             # every block's totals are stored
             return _Done()
         from .parallel import allreduce_each_async
         return allreduce_each_async([self._flat[v] for v in vects],

@@ -318,6 +318,20 @@ int chb_fft_x(const double* in, double* out, uint32_t rows, uint32_t Nx, size_t 
               const double* phase, int phase_on_input, const double* twiddles,
               uint32_t L, const double* chirp, const double* bfft, void* stream);
 
+/* ---------------------------------------------------------------- multi-GPU: peer memory */
+
+/* In-place sum over ranks of one flat FP64 buffer of n doubles that every rank holds as
+ * SYMMETRIC memory: peer_ptrs_host[r] = device address of rank r's buffer as mapped into
+ * this process (world <= 16 entries, 16-byte aligned, n even), multicast_ptr = the
+ * NVSwitch multicast address of the same buffers or 0.  Rank `rank` sums its 1/world
+ * block over all ranks and stores the total into every rank's buffer (P2P loads / stores,
+ * or multimem.ld_reduce / multimem.st when multicast_ptr != 0).  The caller must place a
+ * cross-rank barrier on `stream` before (all partial sums written) and after (all totals
+ * stored) the call.  Used for the E / B partial backward transforms of the kr-row sharded
+ * field solve instead of an NCCL all-reduce; no reference counterpart. */
+int chb_peer_allreduce_f64(const uint64_t* peer_ptrs_host, int world, int rank,
+                           uint64_t multicast_ptr, size_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,6 +26,14 @@ bench sharded "A=0" ""
 bench sharded_hiprio "TORCH_NCCL_HIGH_PRIORITY=1" ""
 bench sharded_tile128 "CHB_DHT_TILE64=0" ""
 
+# 2b. E/B partial sums through own kernels over peer memory instead of NCCL (compiled, never
+#     run before): parity first, then the bench, P2P and NVSwitch-multicast flavours
+for mode in 1 multimem; do
+  CHB_PEER_EXCHANGE=$mode timeout 300 $TR --master-port 29519 tools/sharded_parity.py 2>&1 | tail -2 \
+    | tee gpurun_out/sharded_parity_${N}gpu_peer_$mode.txt
+  bench sharded_peer_$mode "CHB_PEER_EXCHANGE=$mode" ""
+done
+
 # 3. cfg5 (Nx=16384, Nr=1024, M=2, 32 ppc): replicated against sharded solve
 for flag in "--replicated-solve" ""; do
   timeout 600 $TR --master-port 29518 examples/lpa_script_large.py --cfg5 --steps 10 $flag 2>&1 \
