@@ -57,6 +57,7 @@ SIGNATURES = {
                                  _vp, _u32, _vp, _vp, _vp, _vp]),
     "chb_mirror_axpy": (_i32, [_vp, _vp, _dbl, _dbl, _dbl, _dbl, _i32, _sz, _u32, _vp]),
     "chb_peer_allreduce_f64": (_i32, [_vp, _i32, _i32, ctypes.c_uint64, _sz, _vp]),
+    "chb_peer_allgather_f64": (_i32, [_vp, _i32, _i32, ctypes.c_uint64, _sz, _sz, _vp]),
     "chb_fft_max_pow2": (_i32, []),
     "chb_fft_x": (_i32, [_vp, _vp, _u32, _u32, _sz, _sz, _i32, _i32, _i32, _vp, _i32, _vp, _u32, _vp, _vp, _vp]),
 }

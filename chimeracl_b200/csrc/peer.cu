@@ -59,9 +59,58 @@ multimem_allreduce_kernel(double* mc, size_t begin, size_t end) {
   }
 }
 
+// all-gather of row blocks: every rank copies ITS block [begin, end) of the local buffer to
+// the same place in every other rank's buffer (16-byte P2P stores) ...
+__global__ void __launch_bounds__(512)
+peer_push_kernel(const __grid_constant__ PeerBufs bufs, int world, int rank, size_t begin,
+                 size_t end) {
+  const double* __restrict__ src = bufs.p[rank];
+  const size_t stride = (size_t)gridDim.x * blockDim.x * 2;
+  for (size_t i = begin + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2; i < end;
+       i += stride) {
+    const double2 v = *reinterpret_cast<const double2*>(src + i);
+#pragma unroll
+    for (int r = 0; r < kMaxPeers; ++r)
+      if (r < world && r != rank) *reinterpret_cast<double2*>(bufs.p[r] + i) = v;
+  }
+}
+
+// ... or stores it once through the multicast address (the switch fans it out)
+__global__ void __launch_bounds__(512)
+multimem_push_kernel(const double* __restrict__ src, double* mc, size_t begin, size_t end) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < end; i += stride) {
+    const double v = src[i];
+    asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(mc + i), "d"(v) : "memory");
+  }
+}
+
 }  // namespace chb
 
 using namespace chb;
+
+extern "C" int chb_peer_allgather_f64(const uint64_t* peer_ptrs_host, int world, int rank,
+                                      uint64_t multicast_ptr, size_t begin, size_t count,
+                                      void* stream) {
+  if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world || !peer_ptrs_host)
+    return CHB_ERR_ARG;
+  if (count == 0 || world == 1) return CHB_OK;
+  const int grid = 2 * kSMs;
+  if (multicast_ptr) {
+    multimem_push_kernel<<<grid, 512, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const double*>(peer_ptrs_host[rank]),
+        reinterpret_cast<double*>(multicast_ptr), begin, begin + count);
+    CHB_RETURN_LAST_ERROR();
+  }
+  if ((begin & 1) || (count & 1)) return CHB_ERR_ARG;
+  PeerBufs bufs;
+  for (int r = 0; r < kMaxPeers; ++r) {
+    bufs.p[r] = r < world ? reinterpret_cast<double*>(peer_ptrs_host[r]) : nullptr;
+    if (r < world && (peer_ptrs_host[r] & 15)) return CHB_ERR_ARG;
+  }
+  peer_push_kernel<<<grid, 512, 0, (cudaStream_t)stream>>>(bufs, world, rank, begin, begin + count);
+  CHB_RETURN_LAST_ERROR();
+}
 
 extern "C" int chb_peer_allreduce_f64(const uint64_t* peer_ptrs_host, int world, int rank,
                                       uint64_t multicast_ptr, size_t n, void* stream) {

@@ -33,6 +33,16 @@ class _Done:
         pass
 
 
+class _Barrier:
+    """Cross-rank barrier of a symmetric-memory handle, enqueued on the stream by wait()."""
+
+    def __init__(self, handle, channel=0):
+        self.handle, self.channel = handle, channel
+
+    def wait(self):
+        self.handle.barrier(channel=self.channel)
+
+
 class SpectralSharding:
     """kr-row sharded field solve over the ranks of the Communicator's process group (no
     reference counterpart: the reference is single-device).  Every rank keeps full-size
@@ -65,14 +75,38 @@ class SpectralSharding:
         R = spectral_rows(K, 0, world)[2]
         self._sharding = {'world': world, 'rank': rank, 'emulate': bool(emulate), 'R': R,
                           'stores': {}}
+        # CHB_PEER_EXCHANGE=1 | multimem (opt-in, not yet run on hardware): the exchanged
+        # buffers are symmetric memory and the exchanges are own kernels over NVLink peer
+        # memory (csrc/peer.cu: P2P loads / stores, or NVSwitch multimem) between cross-rank
+        # barriers of the symmetric-memory handles, instead of NCCL collectives
+        import ctypes
+        import os
+        peer = os.environ.get('CHB_PEER_EXCHANGE', '0')
+        symm = None
+        if peer != '0' and not emulate and world > 1:
+            import torch.distributed._symmetric_memory as symm
+            self._sharding['peer'] = {}
+
+        def register(key, flat):
+            hdl = symm.rendezvous(flat, group=pg)
+            ptrs = [int(p) for p in hdl.buffer_ptrs]
+            mc = int(getattr(hdl, 'multicast_ptr', 0) or 0) if peer == 'multimem' else 0
+            self._sharding['peer'][key] = (hdl, (ctypes.c_uint64 * world)(*ptrs), mc)
+
         # all-gathered arrays live in storage of world*R >= K rows, so that the chunks
         # are equal; DataDev keeps showing the (K, Nx) prefix under the same key
         Nx = int(self.Args['Nx'])
         for name in ['rho'] + ['G' + c for c in self.Args['vec_comps']]:
             for m in range(self.Args['M'] + 1):
                 key = name + '_fb_m' + str(m)
-                store = torch.zeros((world * R, Nx), dtype=torch.complex128,
-                                    device=self.comm.device)
+                if symm is not None:
+                    flat = symm.empty(world * R * Nx * 2, dtype=torch.float64,
+                                      device=self.comm.device).zero_()
+                    store = torch.view_as_complex(flat.view(world * R * Nx, 2)).view(world * R, Nx)
+                    register(key, flat)
+                else:
+                    store = torch.zeros((world * R, Nx), dtype=torch.complex128,
+                                        device=self.comm.device)
                 store[:K] = self.DataDev[key].t
                 self.DataDev[key] = DevArray(store[:K])
                 self._sharding['stores'][key] = store
@@ -81,16 +115,9 @@ class SpectralSharding:
         # array rides along; the backward transform never writes it and warp_axis
         # overwrites it before the gather reads it.
         shape = (int(self.Args['Nr']), Nx)
-        # CHB_PEER_EXCHANGE=1 | multimem (opt-in, not yet run on hardware): the flat buffers
-        # are symmetric memory and the sum is chb_peer_allreduce_f64 (P2P loads / stores or
-        # NVSwitch multimem) between two cross-rank barriers instead of an NCCL all-reduce
-        import os
-        peer = os.environ.get('CHB_PEER_EXCHANGE', '0')
         alloc = None
-        if peer != '0' and not emulate and world > 1:
-            import torch.distributed._symmetric_memory as symm
+        if symm is not None:
             alloc = lambda n: symm.empty(n, dtype=torch.float64, device=self.comm.device).zero_()  # noqa: E731
-            self._sharding['peer'] = {}
         for v in ('E', 'B'):
             names = [v + c for c in self.Args['vec_comps']]
             old = {n + '_m' + str(m): self.DataDev[n + '_m' + str(m)].t
@@ -99,11 +126,7 @@ class SpectralSharding:
             for key, t in old.items():
                 self.DataDev[key].t.copy_(t)
             if alloc is not None:
-                import ctypes
-                hdl = symm.rendezvous(self._flat[v], group=pg)
-                ptrs = [int(p) for p in hdl.buffer_ptrs]
-                mc = int(getattr(hdl, 'multicast_ptr', 0) or 0) if peer == 'multimem' else 0
-                self._sharding['peer'][v] = (hdl, (ctypes.c_uint64 * world)(*ptrs), mc)
+                register(v, self._flat[v])
         self._shard = None if emulate else _Shard(*spectral_rows(K, rank, world)[:2])
         return self
 
@@ -132,9 +155,20 @@ class SpectralSharding:
         st = self.__dict__.get('_sharding')
         if st is None or st['emulate'] or st['world'] == 1:
             return _Done()
+        keys = [n + '_fb_m' + str(m) for n in names for m in range(self.Args['M'] + 1)]
+        if 'peer' in st:
+            # push the owned rows into every rank's array; the barrier that makes all ranks'
+            # rows visible is only enqueued by .wait(), so the work issued in between runs
+            # ahead of it
+            chunk = st['R'] * int(self.Args['Nx']) * 2
+            own = (self._shard.hi - self._shard.lo) * int(self.Args['Nx']) * 2
+            for key in keys:
+                _, ptrs, mc = st['peer'][key]
+                self._call('chb_peer_allgather_f64', ptrs, st['world'], st['rank'], mc,
+                           st['rank'] * chunk, own)
+            return _Barrier(st['peer'][keys[0]][0])
         from .parallel import allgather_rows_async
-        stores = [st['stores'][n + '_fb_m' + str(m)] for n in names
-                  for m in range(self.Args['M'] + 1)]
+        stores = [st['stores'][k] for k in keys]
         return allgather_rows_async(stores, st['rank'], self.comm.process_group) or _Done()
 
     def reduce_grid_fields(self, vects):

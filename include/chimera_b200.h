@@ -332,6 +332,15 @@ int chb_fft_x(const double* in, double* out, uint32_t rows, uint32_t Nx, size_t 
 int chb_peer_allreduce_f64(const uint64_t* peer_ptrs_host, int world, int rank,
                            uint64_t multicast_ptr, size_t n, void* stream);
 
+/* All-gather of blocks of one symmetric FP64 buffer: this rank's doubles [begin, begin+count)
+ * (begin, count even) are copied to the same place in every other rank's buffer (16-byte P2P
+ * stores, or one multimem.st per element when multicast_ptr != 0).  The caller places a
+ * cross-rank barrier on `stream` after the call of all ranks, before the gathered data is
+ * read.  Used for the rho / G spectra of the kr-row sharded field solve (the owned kr rows
+ * are one contiguous block) instead of an NCCL all-gather; no reference counterpart. */
+int chb_peer_allgather_f64(const uint64_t* peer_ptrs_host, int world, int rank,
+                           uint64_t multicast_ptr, size_t begin, size_t count, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
