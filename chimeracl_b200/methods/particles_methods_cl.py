@@ -124,8 +124,7 @@ class ParticleMethodsCL(GenericMethodsCL):
         npx, npr, npt = (int(v) for v in self.Args['Nppc'])
         ncx, ncr = Nx_loc - 1, Nr_loc - 1
         ncells = ncx * ncr
-        theta_var = torch.rand(ncells, dtype=torch.float64, device=dev,
-                               generator=self.comm.generator) * (2 * np.pi)
+        theta_var = self._theta_offsets(ncells)
         self._fill_grid(theta_var, Xgrid, Rgrid, (npx, npr, npt))
         self.DataDev['w_new'] *= self.Args['w0']
 
@@ -151,6 +150,12 @@ class ParticleMethodsCL(GenericMethodsCL):
                 buf.fill(centre)
             self.DataDev[arg + '_new'] = buf
         self._set_g_inv_new()
+
+    def _theta_offsets(self, ncells):
+        """Per-cell azimuthal offsets of the new lattice, uniform in [0, 2 pi)
+        (reference :80-82, `_fill_arr_rand` on the Threefry stream)."""
+        return torch.rand(ncells, dtype=torch.float64, device=self.comm.device,
+                          generator=self.comm.generator) * (2 * np.pi)
 
     def _fill_grid(self, theta_var, Xgrid, Rgrid, nppc):
         """Regular (x, r, theta) lattice in every cell with a per-cell theta offset:

@@ -15,17 +15,17 @@ from chimeracl_b200.laser import add_gausian_pulse
 from chimeracl_b200.pic_loop import PIC_loop
 
 
-def build(Nx=900, Nr=90, M=1, comm=None):
+def build(Nx=900, Nr=90, M=1, comm=None, Lx=10., x0=0., profile_start=43.1):
     xmin, xmax = -43., 43.
     rmin, rmax = 0., 36.
     a0 = 3
-    Lx, w0 = 10., 12.
-    x0, x_foc = 0., 100.
+    w0 = 12.
+    x_foc = 100.
     dens = 7e18 / (1.1e21 / 0.8 ** 2)
     Npx, Npr, Npth = 2, 2, 4
     frame_velocity = 1.
     frameSteps = 20
-    dens_profiles = [{'coord': 'x', 'points': [-100, 43.1, 90, 5e5], 'values': [0, 0, 1, 1]}, ]
+    dens_profiles = [{'coord': 'x', 'points': [-100, profile_start, 90, 5e5], 'values': [0, 0, 1, 1]}, ]
 
     comm = comm or Communicator(answers=[0, 0])
     grid_in = {'Xmin': xmin, 'Xmax': xmax, 'Nx': Nx, 'Rmin': rmin, 'Rmax': rmax, 'Nr': Nr,

@@ -175,6 +175,64 @@ class OracleParticles:
         self.reset_num_parts()
 
 
+    # ---- particle creation (init / injection path)
+    def make_new_domain(self, parts_in, density_profiles=None, theta_source=None):
+        """particles_methods_cl.py:66-147.  The reference draws the per-cell theta
+        offsets from pyopencl's Threefry stream (:80-82), which is not reproducible
+        (parity unpinned); theta_source(ncells) -> float64[ncells] in
+        [0, 2 pi) injects the table instead, so that both sides of a parity test
+        create the same particles.  Thermal momenta (dpx/dpy/dpz != 0) come from the
+        same stream and are refused here for the same reason."""
+        A = self.Args
+        xmin, xmax, rmin, rmax = (parts_in[k] for k in ("Xmin", "Xmax", "Rmin", "Rmax"))
+        Nx_loc = int(np.ceil((xmax - xmin) / A["dx"]) + 1)
+        Nr_loc = int(np.round((rmax - rmin) / A["dr"]) + 1)
+        Xgrid_loc = xmin + A["dx"] * np.arange(Nx_loc)
+        Rgrid_loc = rmin + A["dr"] * np.arange(Nr_loc)
+        A["right_lim"] = Xgrid_loc[-1]
+        ncells = (Nx_loc - 1) * (Nr_loc - 1)
+        theta = np.ascontiguousarray(theta_source(ncells), dtype=np.float64)
+        assert theta.shape == (ncells,)
+        x, y, z, w = self.K.fill_grid(theta, Xgrid_loc, Rgrid_loc, A["Nppc"])
+        w *= A["w0"]
+        N = self.new = {"x": x, "y": y, "z": z, "w": w}
+        if density_profiles is not None:
+            for profile in density_profiles:
+                if profile["coord"] != "x":
+                    continue
+                self.dens_profile(profile["points"], profile["values"],
+                                  parts_in["Xmin"], parts_in["Xmax"], N["x"], N["w"])
+        if not self.immobile:
+            for a in ("px", "py", "pz"):
+                assert parts_in.get("d" + a, 0) == 0, "thermal momenta: RNG stream unpinned"
+                N[a] = np.full(x.size, float(parts_in.get(a + "_c", 0)))
+            N["g_inv"] = 1.0 / np.sqrt(1 + N["px"] ** 2 + N["py"] ** 2 + N["pz"] ** 2)
+
+    def dens_profile(self, x_prf, f_prf, xmin, xmax, x, w):
+        """particles_methods_cl.py:179-204."""
+        x_prf = np.array(x_prf, dtype=np.double)
+        f_prf = np.array(f_prf, dtype=np.double)
+        i_start = (x_prf < xmin).sum() - 1
+        i_stop = (x_prf < xmax).sum() + 1
+        x_loc = np.ascontiguousarray(x_prf[i_start:i_stop])
+        f_loc = np.ascontiguousarray(f_prf[i_start:i_stop])
+        dxm1_loc = 1.0 / (x_loc[1:] - x_loc[:-1])
+        self.K.profile_by_interpolant(x, w, x_loc, f_loc, dxm1_loc)
+
+    def add_new_particles(self, source=None):
+        """particles_methods_cl.py:40-64: append the *_new arrays (the ions copy the
+        electrons' through InjectorSource)."""
+        src = self.new if source is None else source.new
+        for a in self.attrs:
+            self.D[a] = np.concatenate((self.D[a], src[a]))
+        self.reset_num_parts()
+        self.flag_sorted = False
+
+    def free_added(self):
+        """particles_methods_cl.py:318-325."""
+        self.new = None
+
+
 # ----------------------------------------------------------------------------- solver
 class OracleSolver:
     """grid.py + transformer.py + solver.py and their methods/ mixins."""
@@ -299,6 +357,12 @@ class OracleSolver:
                 self.K.mult_elementwise(self.Args["Poiss_m%d" % m],
                                         self.D["%s%s_fb_m%d" % (fld, c, m)])
 
+    def field_poiss_scl(self, fld):
+        """transformer_methods_cl.py:73-77."""
+        for m in range(self.M + 1):
+            self.K.mult_elementwise(self.Args["Poiss_m%d" % m],
+                                    self.D["%s_fb_m%d" % (fld, m)])
+
     def _get_mm1(self, src_name, comp):
         if self.M == 0:
             return
@@ -413,8 +477,56 @@ class OracleSolver:
         self.field_poiss_vec("B")
 
 
-def pic_step(solver, species):
-    """pic_loop.py:57-142 without frames and diagnostics (out of scope here)."""
+class OracleFrame:
+    """frame.py:4-64: moving window + plasma injector."""
+
+    def __init__(self, cfg, theta_source):
+        self.Args = dict(cfg)
+        for k, v in (("Steps", 1.0), ("Velocity", 0.0), ("dt", 1), ("DensityProfiles", None)):
+            self.Args.setdefault(k, v)
+        self.theta_source = theta_source
+
+    def shift_grids(self, grids, steps=None):
+        """frame.py:22-30 (host Args and the device scalars are one dict here)."""
+        if steps is None:
+            steps = self.Args["Steps"]
+        x_shift = steps * self.Args["dt"] * self.Args["Velocity"]
+        for grid in grids:
+            for arg in ("Xmax", "Xmin"):
+                grid.Args[arg] += x_shift
+            grid.Args["Xgrid"] = grid.Args["Xgrid"] + x_shift
+
+    def inject_plasma(self, species, grid, steps=None):
+        """frame.py:32-64."""
+        if steps is None:
+            steps = self.Args["Steps"]
+        x_shift = steps * self.Args["dt"] * self.Args["Velocity"]
+        for sp in species:
+            if sp.Args["Np"] == 0:
+                sp.Args["right_lim"] = grid.Args["Xmax"] - x_shift
+            dom = {"Xmin": sp.Args["right_lim"]}
+            dom["Xmax"] = dom["Xmin"] + x_shift
+            dom["Rmin"] = grid.Args["Rmin"] * (grid.Args["Rmin"] > 0)
+            dom["Rmax"] = grid.Args["Rmax"]
+            sp.make_new_domain(dom, density_profiles=self.Args["DensityProfiles"],
+                               theta_source=self.theta_source)
+            sp.add_new_particles(sp.Args.get("InjectorSource"))
+        for sp in species:
+            sp.free_added()
+            sp.sort_parts(grid)
+            sp.align_parts()
+            num_ppc = int(np.prod(sp.Args["Nppc"]) + 1)
+            x_max = sp.D["x"][-num_ppc:].max()
+            sp.Args["right_lim"] = x_max + 0.5 * sp.Args["ddx"]
+
+
+def pic_step(solver, species, frames=(), it=0):
+    """pic_loop.py:57-142 (diagnostics are out of scope here); `it` is the loop
+    counter before the step, which decides whether the frames fire (:63-66)."""
+    for frame in frames:
+        if np.mod(it, frame.Args["Steps"]) == 0:
+            frame.shift_grids([solver])
+            frame.inject_plasma(species, solver)
     for p in species:
         p.push_coords("half")
         p.sort_parts(solver)

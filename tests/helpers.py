@@ -56,3 +56,41 @@ def rel_err(a, b):
     s = np.abs(b).max() if b.size else 0.0
     d = np.abs(a - b).max() if b.size else 0.0
     return 0.0 if d == 0 else d / max(s, 1e-300)
+
+
+def per_particle_rel_err(got, ref):
+    """Worst PER-PARTICLE relative error of the momentum vector, |dp| / |p_ref| of that
+    particle, and of g_inv (not normalised by an array-wide maximum)."""
+    if ref["px"].size == 0:
+        return 0.0, 0.0
+    d2 = sum((np.asarray(got[k]) - ref[k]) ** 2 for k in ("px", "py", "pz"))
+    n2 = sum(ref[k] ** 2 for k in ("px", "py", "pz"))
+    ep = float(np.sqrt(d2 / np.maximum(n2, 1e-300)).max())
+    eg = float((np.abs(np.asarray(got["g_inv"]) - ref["g_inv"]) / np.abs(ref["g_inv"])).max())
+    return ep, eg
+
+
+def moments(D):
+    """Particle moments compared over N-step runs: sum w, sum w p_k,
+    sum w (gamma - 1); w_abs_p = sum |w| |p| is the scale the momentum sums are
+    compared on (they cancel to ~0 in a symmetric plasma)."""
+    w = D["w"]
+    out = {"w": float(w.sum())}
+    p2 = 0
+    for k in ("px", "py", "pz"):
+        out["w" + k] = float((w * D[k]).sum())
+        p2 = p2 + D[k] ** 2
+    out["w_abs_p"] = float((np.abs(w) * np.sqrt(p2)).sum())
+    out["w_kin"] = float((w * (np.sqrt(1 + p2) - 1)).sum())
+    return out
+
+
+def field_energy(F, A):
+    """sum over modes of |E|^2 + |B|^2, weighted by the ring volume r dr dx (m >= 1
+    modes count twice: +m and -m)."""
+    r = A["Rgrid"][1:, None]
+    tot = 0.0
+    for k, v in F.items():
+        m = int(k.split("_m")[1])
+        tot += (1 if m == 0 else 2) * float((np.abs(v[1:]) ** 2 * r).sum())
+    return tot * A["dx"] * A["dr"] * 2 * np.pi

@@ -377,6 +377,83 @@ def test_laser_group_velocity(comm):
     assert abs(veloc.mean() - theory) / theory < 0.1
 
 
+@pytest.mark.parametrize("M,Nx", [(0, 256), (1, 900)])
+def test_laser_initialiser_matches_oracle(comm, M, Nx):
+    """add_gausian_pulse (reference laser.py:3-37) on the CUDA path against
+    oracle.orchestration.add_gaussian_pulse: Ez_fb_m0, Gz_fb_m0, the restored B spectra and
+    all E / B grids <= 1e-12 of the pulse amplitude (Nx = 900: cfg1's Bluestein FFT)."""
+    from chimeracl_b200.laser import add_gausian_pulse
+    from chimeracl_b200.solver import Solver
+    cfg = {"Xmin": -43.0, "Xmax": 43.0, "Nx": Nx, "Rmin": 0.0, "Rmax": 36.0, "Nr": 90, "M": M,
+           "DampCells": 50}
+    cfg["dt"] = (cfg["Xmax"] - cfg["Xmin"]) / cfg["Nx"]
+    laser = {"k0": 1.0, "a0": 3.0, "x0": 2.0, "Lx": 10.0, "R": 12.0, "x_foc": 100.0}
+    S = Solver(dict(cfg), comm)
+    add_gausian_pulse(S, dict(laser))
+    So = O.OracleSolver(dict(cfg), NumpyKernels(M))
+    O.add_gaussian_pulse(So, dict(laser))
+    assert np.abs(So.D["Ez_m0"]).max() > 1.0
+    for k in ("Ez_fb_m0", "Gz_fb_m0", "Bx_fb_m0", "By_fb_m0", "Bz_fb_m0"):
+        scale = np.abs(So.D["Ez_fb_m0" if k[0] == "E" else
+                            "Gz_fb_m0" if k[0] == "G" else "By_fb_m0"]).max()
+        assert np.abs(S.DataDev[k].get() - So.D[k]).max() / scale < 1e-12, k
+    for f in "EB":
+        scale = max(np.abs(So.D["%s%s_m0" % (f, c)]).max() for c in "xyz")
+        for c in "xyz":
+            for m in range(M + 1):
+                k = "%s%s_m%d" % (f, c, m)
+                assert np.abs(S.DataDev[k].get()[1:] - So.D[k][1:]).max() / scale < 1e-12, k
+
+
+@pytest.mark.parametrize("M", [0, 1, 2])
+def test_field_poiss_scl(comm, M):
+    """field_poiss_scl (reference transformer_methods_cl.py:73-77): spectrum times
+    Poiss_m = 1 / w_m^2, per mode; one multiplication per element -> bit-exact."""
+    from chimeracl_b200.solver import Solver
+    cfg = {"Xmin": -2.0, "Xmax": 3.0, "Nx": 96, "Rmin": 0.0, "Rmax": 4.0, "Nr": 37, "M": M}
+    S = Solver(dict(cfg), comm)
+    So = O.OracleSolver(dict(cfg), NumpyKernels(M))
+    rng = np.random.default_rng(40 + M)
+    for m in range(M + 1):
+        k = "rho_fb_m%d" % m
+        a = rng.normal(size=So.D[k].shape) + 1j * rng.normal(size=So.D[k].shape)
+        So.D[k][...] = a
+        S.DataDev[k][:] = a
+    S.field_poiss_scl("rho")
+    So.field_poiss_scl("rho")
+    for m in range(M + 1):
+        k = "rho_fb_m%d" % m
+        assert np.array_equal(S.DataDev[k].get(), So.D[k]), k
+
+
+def test_phase_timer_keys(comm):
+    """PIC_loop(timit=True) (reference pic_loop.py:5-8, 42-55): the Timer dict carries
+    exactly the reference's phase keys, in seconds, and the phases add up to the step."""
+    import torch
+    from chimeracl_b200.pic_loop import PIC_loop, loop_steps
+    assert loop_steps == ["frame", "push-x", "sort", "depose", "transform", "smooth",
+                          "data_copy", "grad", "push-eb", "damp-eb", "restore_B",
+                          "gather + push-p"]
+    G = load_golden(1)
+    S, P, I = gpu_case_from_golden(G, comm)
+    loop = PIC_loop(solvers=[S], species=[P, I], timit=True)
+    assert list(loop.Timer) == loop_steps and not any(loop.Timer.values())
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(3):
+        loop.step()
+    t1.record()
+    T = loop.timer_collect()
+    assert list(T) == loop_steps
+    total = t0.elapsed_time(t1) * 1e-3
+    assert all(v >= 0 for v in T.values())
+    for k in ("sort", "depose", "transform", "grad", "push-eb", "damp-eb", "restore_B",
+              "gather + push-p"):
+        assert T[k] > 0, k
+    assert 0.3 * total < sum(T.values()) <= total * 1.001
+
+
 # ----------------------------------------------------------------------------- moving window
 def test_lwfa_moving_window_run(comm):
     """examples/lpa_script_small.py at reduced size for 45 steps: laser initialiser,

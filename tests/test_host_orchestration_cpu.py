@@ -9,6 +9,7 @@ import pytest
 
 import cabi_emulator as emu
 import test_gpu_parity as gpu_tests
+import test_gpu_parity_shapes as shape_tests
 
 CASES = [
     ("test_push_and_sort_bit_exact", dict(M=0, fused=False)),
@@ -40,3 +41,23 @@ def test_host_side_of_gpu_test(monkeypatch, name, kwargs):
     comm = emu.EmulatedComm()
     monkeypatch.setattr(real_lib, "_lib", comm.lib)
     getattr(gpu_tests, name)(comm, **kwargs)
+
+
+# bodies of tests/test_gpu_parity_shapes.py at reduced sizes: the oracle Frame restatement
+# against the product's moving window + injector, the cfg3-shape full steps, the uneven-
+# filling particle sequence -- host logic only, see the module docstring
+SHAPE_CASES = [
+    ("test_particle_kernels_long_rows_uneven_filling", dict(M=1, Nx=160, Nr=80, n=60000)),
+    ("test_cfg3_shape_two_steps_against_reference_kernels", dict(Nx=128, Nr=40)),
+    ("test_cfg1_lwfa_moving_window_against_oracle", dict(Nx=200, Nr=30, checkpoints=(1, 20, 21))),
+]
+
+
+@pytest.mark.filterwarnings("ignore:invalid value encountered in cast")
+@pytest.mark.parametrize("name,kwargs", SHAPE_CASES, ids=[n[5:] for n, _ in SHAPE_CASES])
+def test_host_side_of_shape_test(monkeypatch, name, kwargs):
+    from chimeracl_b200 import _lib as real_lib
+    emu.patch_cuda_host_calls(monkeypatch)
+    comm = emu.EmulatedComm()
+    monkeypatch.setattr(real_lib, "_lib", comm.lib)
+    getattr(shape_tests, name)(comm, **kwargs)
