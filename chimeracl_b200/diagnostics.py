@@ -38,16 +38,31 @@ class Diagnostics:
         self.info_str = 'info/'
         self.generic_keys = ['Xgrid', 'Rgrid', 'dx', 'dr', 'dt', 'Nx', 'Nr', 'M']
 
+        # multi-GPU (one process per rank): the fields are complete on every rank after
+        # the solver's collectives, so rank 0 alone writes them (and cleans the directory);
+        # the species arrays are each rank's particle shard and go to per-rank files
+        comm = getattr(solver, 'comm', None)
+        self.rank = int(getattr(comm, 'rank', 0))
+        self.world = int(getattr(comm, 'world_size', 1))
+        self._group = getattr(comm, 'process_group', None)
+
         self.path = os.path.join(os.getcwd(), path) + '/'
-        if not os.path.exists(self.path):
-            os.makedirs(self.path)
-        else:
-            for fl in os.listdir(self.path):
-                os.remove(self.path + fl)
+        if self.rank == 0:
+            if not os.path.exists(self.path):
+                os.makedirs(self.path)
+            else:
+                for fl in os.listdir(self.path):
+                    os.remove(self.path + fl)
+        self._barrier()
 
         self.Args.setdefault('ScalarFields', [])
         self.Args.setdefault('VectorFields', [])
         self.Args.setdefault('Species', {'Components': [], })
+
+    def _barrier(self):
+        if self._group is not None and self.world > 1:
+            import torch.distributed as dist
+            dist.barrier(group=self._group)
 
     # ------------------------------------------------------------------ record
     def make_record(self, it):
@@ -56,13 +71,20 @@ class Diagnostics:
         self.record = {}
         self.record[self.base_str + self.info_str + 'iteration'] = it
         self.add_generic_info()
+        # every rank takes part in the deposits / transforms (they are collective) ...
         for fld in self.Args['ScalarFields']:
             self.add_field(fld)
         for fld in self.Args['VectorFields']:
             for comp in ['x', 'y', 'z']:
                 self.add_field(fld + comp)
         self.add_species()
-        self._write(str(it).rjust(9, '0'))
+        stem = str(it).rjust(9, '0')
+        if self.rank > 0:
+            # ... but only rank 0 writes the fields; the others write their species shard
+            flds = self.base_str + self.flds_str
+            self.record = {k: v for k, v in self.record.items() if not k.startswith(flds)}
+            stem += '_rank%d' % self.rank
+        self._write(stem)
         self.record = None
 
     def _write(self, stem):

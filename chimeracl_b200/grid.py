@@ -73,6 +73,10 @@ class Grid(GridMethodsCL):
         pending = self.__dict__.pop('_pending_J', None)
         if pending is None:
             return
+        # a bounded cell-changer queue (more particles than a quarter of the device memory
+        # holds records for) must not have overflowed: checked here, before J is consumed
+        for parts in self.__dict__.pop('_fused_species', ()):
+            parts._check_exception_overflow()
         if pending is not True:
             pending.wait()
         self.postproc_depose_vector('J', reduce=False)
@@ -92,6 +96,11 @@ class Grid(GridMethodsCL):
             self.depose_vector(parts, ['p' + comp for comp in comps], ['g_inv', 'w'], 'J',
                                charge=parts.Args['charge'], push_dt=push_dt,
                                second_push_index=(push_mode == 'half+half'))
+            if push_dt is not None:
+                self.__dict__.setdefault('_fused_species', []).append(parts)
+        if not defer:
+            for parts in self.__dict__.pop('_fused_species', ()):
+                parts._check_exception_overflow()
         if defer:
             # the sum over ranks runs while the caller goes on (second push + sort);
             # finish_currents() must be called before J is used

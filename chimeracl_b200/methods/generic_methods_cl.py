@@ -69,6 +69,7 @@ class Communicator:
         self.thr = _Thread(self)
         self.dev_type = "GPU"
         self.dev_name = torch.cuda.get_device_name(self.device)
+        self.device_memory_bytes = int(torch.cuda.get_device_properties(self.device).total_memory)
         self.plat_name = "NVIDIA"
         self.ocl_version = "CUDA sm_%d%d" % torch.cuda.get_device_capability(self.device)
         self.fft_method = "chimera_b200"

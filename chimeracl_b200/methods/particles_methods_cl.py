@@ -54,12 +54,17 @@ class ParticleMethodsCL(GenericMethodsCL):
     def exception_workspace(self):
         """(pointer, bytes) of the scratch chb_push_depose_vector / _push_index need: the
         queue of the particles that changed cell.  Sized for the worst case (one 64-byte
-        record per particle) up to 4 GiB; beyond that a quarter of the particles, with the
-        device-side counter read back asynchronously and checked before the next use
-        (an overflow means the previous step's current was incomplete: raise)."""
+        record per particle) up to a quarter of the device memory; beyond that a quarter of
+        the particles, with the device-side counter read back asynchronously and checked
+        by Grid.finish_currents() BEFORE the deposited current is used in the same step
+        (an overflow means that current is incomplete: raise)."""
         Np = int(self.Args['Np'])
         full = int(self._lib.chb_push_depose_workspace_bytes(Np))
-        limit = getattr(self, '_exc_full_limit', 4 << 30)
+        limit = getattr(self, '_exc_full_limit', None)
+        if limit is None:
+            # worst case (every particle changes cell) as long as it takes at most a quarter
+            # of the device memory: 64 B per particle, 34 GB for 5.4e8 particles on 180 GB
+            limit = getattr(self.comm, 'device_memory_bytes', 16 << 30) // 4
         nbytes = full if full <= limit else 16 + 64 * (Np // 4 + 4096)
         self._check_exception_overflow()
         ws = self._buf('exc_ws', (nbytes + 7) // 8, np.double)

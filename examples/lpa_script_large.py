@@ -23,19 +23,10 @@ from chimeracl_b200.pic_loop import PIC_loop
 from chimeracl_b200.parallel import init_distributed
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--cfg5", action="store_true")
-    ap.add_argument("--steps", type=int, default=60)
-    ap.add_argument("--replicated-solve", action="store_true",
-                    help="multi-GPU: every rank runs the whole field solve (default: kr-row sharded)")
-    a = ap.parse_args()
-    comm = Communicator(answers=[0, 0])
-    init_distributed(comm)
+def build(comm, cfg5=False, replicated_solve=False):
     rank, world = comm.rank, comm.world_size
-
     xmin, xmax, rmax = -100., 40., 50.
-    if a.cfg5:
+    if cfg5:
         Nx, Nr, M, nppc = 16384, 1024, 2, (2, 4, 4)
     else:
         Nx, Nr, M, nppc = 4096, 252, 1, (2, 2, 4)
@@ -58,7 +49,7 @@ def main():
     ions.Args['InjectorSource'] = eons
 
     frames = []
-    if a.cfg5:
+    if cfg5:
         # plasma pre-filled over the box; every rank fills its own x-slab
         A = solver.Args
         ncx = A['Nx'] - 3
@@ -76,10 +67,25 @@ def main():
     else:
         frames = [Frame({'Velocity': 1., 'dt': solver.Args['dt'], 'Steps': 20,
                          'DensityProfiles': dens_profiles})]
-    if world > 1 and not a.replicated_solve:
+    if world > 1 and not replicated_solve:
         # after the laser initialiser: the spectra it wrote are complete on every rank
         solver.enable_spectral_sharding()
     loop = PIC_loop(solvers=[solver, ], species=[eons, ions], frames=frames, diags=[])
+    return solver, eons, ions, loop
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cfg5", action="store_true")
+    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--replicated-solve", action="store_true",
+                    help="multi-GPU: every rank runs the whole field solve (default: kr-row sharded)")
+    a = ap.parse_args()
+    comm = Communicator(answers=[0, 0])
+    init_distributed(comm)
+    rank, world = comm.rank, comm.world_size
+    solver, eons, ions, loop = build(comm, a.cfg5, a.replicated_solve)
+    Nx, Nr, M = solver.Args['Nx'], solver.Args['Nr'], solver.Args['M']
 
     for _ in range(3):
         loop.step()

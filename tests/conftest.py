@@ -3,6 +3,10 @@ import sys
 
 import pytest
 
+# the oracle alternates OpenMP kernels (oracle/_ref) with OpenBLAS calls: with libgomp's
+# default active waiting the two thread pools fight for the cores (several times slower)
+os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

@@ -753,6 +753,56 @@ def test_host_buffer_step(comm, overlap):
     assert loop.on_coordinates_final is None
 
 
+def test_host_buffer_pipeline_equals_single_steps(comm):
+    """host_api.HostStepPipeline (upload of step k+1 and download of step k overlapped with
+    the compute of step k on two device buffer sets): every step's host results must be
+    the same as for the same steps run one by one through step_from_host
+    (coordinates bit-exact, momenta / rho to the rounding of the atomics' order)."""
+    import torch
+    from chimeracl_b200 import host_api
+    from chimeracl_b200.solver import Solver
+    from chimeracl_b200.pic_loop import PIC_loop
+    cfg = {"Xmin": -1.0, "Xmax": 1.0, "Nx": 256, "Rmin": 0.0, "Rmax": 1.0, "Nr": 64, "M": 1,
+           "DampCells": 8}
+    nsteps = 5
+    rng = np.random.default_rng(5)
+
+    def fresh():
+        S = Solver(dict(cfg), comm)
+        P, _ = _random_species(comm, 400000, (-0.9, 0.9), seed=22, spread=0.3)
+        P.sort_parts(S)
+        loop = PIC_loop(solvers=[S], species=[P])
+        loop.step()
+        return S, P, loop
+
+    S, P, loop = fresh()
+    host_in, out0 = host_api.make_host_buffers(P, S)
+    # a different batch every step (the pipeline must not mix them up)
+    batches = []
+    for k in range(nsteps):
+        b = {a: host_in[a].clone().pin_memory() for a in host_api.ATTRS_IN}
+        b["px"] += torch.from_numpy(rng.normal(0, 0.01, b["px"].numel()))
+        batches.append(b)
+    ref = []
+    for k in range(nsteps):
+        host_api.step_from_host(loop, P, batches[k], out0)
+        torch.cuda.synchronize()
+        ref.append({a: out0[a].clone() for a in out0})
+    S, P, loop = fresh()
+    outs = [{a: torch.empty_like(out0[a]).pin_memory() for a in out0} for _ in range(nsteps)]
+    pipe = host_api.HostStepPipeline(loop, P)
+    for k in range(nsteps):
+        h2d, d2h = pipe.submit(batches[k], outs[k])
+    pipe.drain()
+    torch.cuda.synchronize()
+    assert h2d == 8 * 8 * P.Args["Np"] and d2h == 7 * 8 * P.Args["Np"] + 8 * 256 * 64
+    for k in range(nsteps):
+        for a in ("x", "y", "z"):          # pushed from the uploaded batch: bit-exact
+            assert torch.equal(outs[k][a], ref[k][a]), (k, a)
+        for a in ("px", "py", "pz", "g_inv", "rho_m0"):   # through the deposits' atomics
+            assert rel_err(outs[k][a].numpy(), ref[k][a].numpy()) < 1e-11, (k, a)
+
+
 def test_cell_changer_queue_overflow_is_detected(comm):
     """With more than 4 GiB of worst-case queue the fused pass gets a quarter-size queue
     and the device counter is checked before the next use: an overflow (incomplete J)
