@@ -182,6 +182,7 @@ def run_reference(args, as_baseline=False):
     from oracle.ref_kernels import RefKernels, ref_available
     from oracle.np_kernels import NumpyKernels
     cores = os.cpu_count() or 1
+    O.FFT_WORKERS = cores            # x-FFTs over the rows on all cores (scipy.fft pocketfft)
     M = 1
     if ref_available(M):
         K = RefKernels(M, parallel=True)

@@ -20,6 +20,19 @@ Parity pin: see oracle/np_kernels.py header.
 import numpy as np
 from scipy.special import jn, jn_zeros
 
+# Threads for the x-FFTs.  None: np.fft (single-threaded; what the parity tests use).
+# bench.py's CPU legs set it to the core count (scipy.fft, the same pocketfft algorithm run
+# over the rows in parallel), so that the timed baseline uses all host cores in every phase.
+FFT_WORKERS = None
+
+
+def _fft(a, inverse=False):
+    if FFT_WORKERS is None:
+        return np.fft.ifft(a, axis=1) if inverse else np.fft.fft(a, axis=1)
+    import scipy.fft
+    f = scipy.fft.ifft if inverse else scipy.fft.fft
+    return f(a, axis=1, workers=FFT_WORKERS)
+
 
 # ----------------------------------------------------------------------------- configs
 def grid_args(cfg):
@@ -328,14 +341,14 @@ class OracleSolver:
                 buf = np.ascontiguousarray(src)
                 if mode == "full":
                     buf = np.dot(A["DHT_m%d" % m], buf)
-                out = np.fft.fft(buf.astype(np.complex128), axis=1)
+                out = _fft(buf.astype(np.complex128))
                 out = np.ascontiguousarray(out)
                 K.multiply_by_phase(out, phs, Nx)
                 D["%s_fb_m%d" % (name, m)][...] = out
             else:
                 buf = D["%s_fb_m%d" % (name, m)].copy()
                 K.multiply_by_phase(buf, phs, Nx)
-                buf = np.ascontiguousarray(np.fft.ifft(buf, axis=1))
+                buf = np.ascontiguousarray(_fft(buf, inverse=True))
                 if m == 0:
                     tmp = np.empty(buf.shape)
                     K.cast_c2d(buf, tmp)

@@ -804,9 +804,10 @@ def test_host_buffer_pipeline_equals_single_steps(comm):
 
 
 def test_cell_changer_queue_overflow_is_detected(comm):
-    """With more than 4 GiB of worst-case queue the fused pass gets a quarter-size queue
-    and the device counter is checked before the next use: an overflow (incomplete J)
-    must raise instead of passing silently; a sufficient queue must not."""
+    """When the worst-case queue would take more than a quarter of the device memory the
+    fused pass gets a quarter-size queue and the device counter is checked in the SAME
+    step, before the deposited current is used: an overflow (incomplete J) must raise
+    instead of passing silently; a sufficient queue must not."""
     from chimeracl_b200.solver import Solver
     from chimeracl_b200.particles import Particles
     cfg = {"Xmin": -1.0, "Xmax": 1.0, "Nx": 48, "Rmin": 0.0, "Rmax": 1.0, "Nr": 24, "M": 1}
@@ -827,11 +828,13 @@ def test_cell_changer_queue_overflow_is_detected(comm):
         return S, P
 
     S, P = make(2.0)                           # ~40 % change cell: 48 k > n/4 + 4096
-    S.depose_currents([P], push_mode="half")
     with pytest.raises(RuntimeError, match="changed cell"):
-        P.exception_workspace()
+        S.depose_currents([P], push_mode="half")      # checked before J is post-processed
+    S, P = make(2.0)
+    S.depose_currents([P], push_mode="half", defer=True)
+    with pytest.raises(RuntimeError, match="changed cell"):
+        S.finish_currents()                    # deferred (PIC_loop): checked before J is used
     S, P = make(0.02)                          # slow particles: a few per cent
-    S1 = Solver(dict(cfg), comm)
     S.depose_currents([P], push_mode="half")
     P.exception_workspace()                    # no overflow -> no exception
 

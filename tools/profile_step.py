@@ -12,6 +12,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--small", action="store_true")
+    ap.add_argument("--presteps", type=int, default=30,
+                    help="unprofiled steps first: the lattice start (16 per cell exactly, nobody "
+                         "changes cell for ~25 steps) is not the steady state")
     a = ap.parse_args()
     import torch
     from chimeracl_b200.methods.generic_methods_cl import Communicator
@@ -30,7 +33,8 @@ def main():
         p.sort_parts(solver)
         p.align_parts()
     loop = PIC_loop(solvers=[solver], species=[eons, ions])
-    loop.step()          # the first step cannot use the fused push+deposit (no previous sort)
+    for _ in range(max(1, a.presteps)):   # (the first step cannot use the one-pass particle side)
+        loop.step()
     torch.cuda.synchronize()
     torch.cuda.profiler.start()
     for _ in range(a.steps):
