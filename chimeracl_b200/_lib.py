@@ -31,8 +31,7 @@ SIGNATURES = {
     "chb_dht_tile_columns": (_i32, [_u32, _u32, _i32]),
     "chb_dmma_peak": (_i32, [_vp, _sz, _i32, _vp, _vp]),
     "chb_push_depose_workspace_bytes": (_sz, [_u32]),
-    "chb_push_depose_push_index": (_i32, [_i32] + [_vp] * 11 + [_u32, _i32, _u32, _u32] + [_vp] * 4 + [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "chb_sort_scatter_incremental": (_i32, [_vp] * 6 + [_u32, _u32, _vp, _sz, _vp]),
+    "chb_push_depose_push_index": (_i32, [_i32] + [_vp] * 11 + [_u32, _i32, _u32, _u32] + [_vp] * 4 + [_vp, _vp, _vp, _vp, _sz, _vp]),
     "chb_postproc_depose": (_i32, [_vp, _vp, _i32, _u32, _u32, _vp, _vp]),
     "chb_warp_axis": (_i32, [_vp, _vp, _i32, _u32, _vp]),
     "chb_gather_push": (_i32, [_i32] + [_vp] * 10 + [_u32, _vp, _u32, _u32] + [_vp] * 4 + [_vp, _vp]),
@@ -136,7 +135,6 @@ def load():
 
 # kernel launches behind each C-ABI call (bench.py reports the total as gpu_launches)
 KERNELS_PER_CALL = {"chb_cell_offsets": 3, "chb_sort_scatter_stable": 3, "chb_align": 2,
-                    "chb_sort_scatter_incremental": 3,
                     "chb_push_depose_vector": 2, "chb_push_depose_push_index": 2}
 CALL_COUNTS = {}
 

@@ -84,15 +84,7 @@ struct DepArgs {
   // coordinates are produced in the same pass (what chb_push_index would do next)
   uint32_t* indx_in_cell;
   uint32_t* sum_in_cell;
-  // PUSH == 2, optional (both or none): products for the incremental re-sort
-  // (chb_sort_scatter_incremental).  rank_out[i] = number of particles of i's cell that
-  // precede it in the previous (stable) order AND stay in that cell -- the final slot of
-  // i inside its cell if nobody moves INTO the cell -- or kMover if i changes cell;
-  // dirty[c] = 1 for every cell that receives a mover.
-  uint32_t* rank_out;
-  unsigned char* dirty;
 };
-constexpr uint32_t kMover = 0xffffffffu;
 
 __device__ __forceinline__ bool cell_valid(int ix, int ir, const GridVals& g) {
   return ix > 0 && ix < g.Nx - 2 && ir < g.Nr - 2 && ir >= 0;
@@ -214,25 +206,6 @@ depose_kernel(const __grid_constant__ DepArgs<M, VEC> a) {
   const uint32_t c1 = min(c0 + (uint32_t)kDepCells, a.ncells);
   const uint32_t P0 = a.cell_offset[c0], P1 = a.cell_offset[c1];
   if (P0 == P1) return;
-  // incremental re-sort products (PUSH == 2): only for CTAs whose particles fit ONE batch
-  // (flat position q = j - P0 < kDepBatch); crowded CTAs declare everybody a mover
-  constexpr bool RK = PUSH == 2;
-  __shared__ uint32_t s_off[RK ? kDepCells + 1 : 1];          // cell starts, relative to P0
-  __shared__ uint32_t s_stay[RK ? (kDepBatch + 31) / 32 : 1];  // stayer bit per flat position
-  const bool ranked = RK && a.rank_out != nullptr;
-  const bool one_batch = P1 - P0 <= (uint32_t)kDepBatch;
-  if (ranked && one_batch) {
-    if (threadIdx.x <= (unsigned)kDepCells)
-      s_off[threadIdx.x] = a.cell_offset[min(c0 + threadIdx.x, c1)] - P0;
-    __syncthreads();
-  }
-  uint32_t c2v[RK ? KP : 1];                                  // new cell of my staged particles
-  // PUSH: cell changers of the batch are first marked in shared memory; the CTA then
-  // reserves ONE range of the global queue (a counter every changer bumped by itself
-  // was the hottest address of the kernel: ~5e5 same-address atomics with a dependent
-  // return value per step) and the staging threads write the records
-  __shared__ uint32_t s_exc[PUSH ? (kDepBatch + 31) / 32 : 1];
-  __shared__ uint32_t s_exc_base;
 
   const int comp = threadIdx.x / kDepCells;           // warp-uniform
   const uint32_t c = c0 + (threadIdx.x - comp * kDepCells);
@@ -317,10 +290,6 @@ depose_kernel(const __grid_constant__ DepArgs<M, VEC> a) {
           a.xw[s] = x2; a.yw[s] = y2; a.zw[s] = z2;
           cell2 = cell_index(x2, y2, z2, g);
           a.indx_in_cell[s] = cell2;
-          if (ranked && !one_batch) {
-            a.rank_out[s] = kMover;
-            a.dirty[cell2] = 1;
-          }
         } else {
           a.xw[s] = xp; a.yw[s] = yp; a.zw[s] = zp;
         }
@@ -338,50 +307,6 @@ depose_kernel(const __grid_constant__ DepArgs<M, VEC> a) {
       }
       }
       if (PUSH == 2) histogram_add(cell2, valid, a.sum_in_cell);
-      if (RK) {
-        c2v[k] = cell2;
-        if (ranked && one_batch) {
-          // old cell of flat position q: the last cell start <= q (upper bound - 1)
-          const uint32_t qpos = threadIdx.x + k * NT;
-          int lo = 0, hi = kDepCells;
-          while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (s_off[mid] <= qpos) lo = mid; else hi = mid - 1;
-          }
-          const bool stay = valid && cell2 == c0 + (uint32_t)lo;
-          const unsigned bits = __ballot_sync(0xffffffffu, stay);
-          if (lane == 0) s_stay[qpos >> 5] = bits;
-        }
-      }
-    }
-  };
-  // after the barrier that follows convert(): ranks of my staged particles
-  auto write_ranks = [&]() {
-#pragma unroll
-    for (int k = 0; k < KP; ++k) {
-      const uint32_t qpos = threadIdx.x + k * NT;
-      if (!(qpos < (uint32_t)kDepBatch) || P0 + qpos >= P1) continue;
-      const uint32_t s = sprev[k];
-      int lo = 0, hi = kDepCells;
-      while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (s_off[mid] <= qpos) lo = mid; else hi = mid - 1;
-      }
-      if (c2v[k] != c0 + (uint32_t)lo) {
-        a.rank_out[s] = kMover;
-        a.dirty[c2v[k]] = 1;
-        continue;
-      }
-      // stayers in [cell start, q)
-      const uint32_t b = s_off[lo];
-      uint32_t r = 0;
-      for (uint32_t wd = b >> 5; wd <= (qpos >> 5); ++wd) {
-        uint32_t m = s_stay[wd];
-        if (wd == (b >> 5)) m &= 0xffffffffu << (b & 31);
-        if (wd == (qpos >> 5)) m &= (1u << (qpos & 31)) - 1u;
-        r += __popc(m);
-      }
-      a.rank_out[s] = r;
     }
   };
 
@@ -399,13 +324,7 @@ depose_kernel(const __grid_constant__ DepArgs<M, VEC> a) {
     }
     cp_async_wait_all();          // this thread's copies of batch b0 have landed
     convert(b0, buf);
-    if (PUSH) {
-      if (threadIdx.x < (kDepBatch + 31) / 32) s_exc[threadIdx.x] = 0;
-    }
     __syncthreads();              // batch b0 ready for everyone; batch b0-1 fully consumed
-    if (RK) {
-      if (ranked && one_batch) write_ranks();
-    }
     if (DB && b1 < P1) {          // overlap: stage the next batch while accumulating this one
       issue(b1, buf ^ 1);
       if (b1 + kDepBatch < P1) load_sidx(b1 + kDepBatch);
@@ -423,7 +342,14 @@ depose_kernel(const __grid_constant__ DepArgs<M, VEC> a) {
         // floor(ax) == ix  <=>  0 <= ax - ix < 1 (the subtraction is exact): a particle
         // that left this cell during the push goes to the exception list instead
         if (!(sX1 >= 0.0 && sX1 < 1.0 && sR1 >= 0.0 && sR1 < 1.0)) {
-          if (comp == 0) atomicOr(&s_exc[(j - b0) >> 5], 1u << ((j - b0) & 31));
+          if (comp == 0) {
+            const uint32_t e = atomicAdd(a.exc_count, 1u);
+            if (e < a.exc_cap) {
+              double* rec = a.exc_rec + (size_t)e * 8;
+#pragma unroll
+              for (int sl = 0; sl < 8; ++sl) rec[sl] = slot(buf, sl, p);
+            }
+          }
           continue;
         }
       }
@@ -472,33 +398,6 @@ depose_kernel(const __grid_constant__ DepArgs<M, VEC> a) {
             accm[m][n][0] = fma(pj[n], er[m], accm[m][n][0]);
             accm[m][n][1] = fma(pj[n], ei[m], accm[m][n][1]);
           }
-        }
-      }
-    }
-    if (PUSH) {
-      // ---------------- queue this batch's cell changers
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        uint32_t tot = 0;
-#pragma unroll
-        for (int wd = 0; wd < (kDepBatch + 31) / 32; ++wd) tot += __popc(s_exc[wd]);
-        s_exc_base = tot ? atomicAdd(a.exc_count, tot) : 0u;
-      }
-      __syncthreads();
-      const uint32_t ebase = s_exc_base;
-#pragma unroll
-      for (int k = 0; k < KP; ++k) {
-        const uint32_t qpos = threadIdx.x + k * NT;
-        if (!(qpos < (uint32_t)kDepBatch)) continue;
-        const uint32_t wd = qpos >> 5, bit = 1u << (qpos & 31);
-        if (!(s_exc[wd] & bit)) continue;
-        uint32_t e = ebase + __popc(s_exc[wd] & (bit - 1u));
-        for (uint32_t v = 0; v < wd; ++v) e += __popc(s_exc[v]);
-        if (e < a.exc_cap) {
-          const int p = pidx((int)qpos);
-          double* rec = a.exc_rec + (size_t)e * 8;
-#pragma unroll
-          for (int sl = 0; sl < 8; ++sl) rec[sl] = slot(buf, sl, p);
         }
       }
     }
@@ -562,10 +461,6 @@ depose_push_tail_kernel(const __grid_constant__ DepArgs<M, true> a) {
       const uint32_t cell2 = cell_index(x2, y2, z2, g);
       a.indx_in_cell[s] = cell2;
       atomicAdd(&a.sum_in_cell[cell2], 1u);
-      if (a.rank_out) {            // old trash-bin particles: always through the slow path
-        a.rank_out[s] = kMover;
-        a.dirty[cell2] = 1;
-      }
     } else {
       a.xw[s] = xp; a.yw[s] = yp; a.zw[s] = zp;
     }
@@ -675,7 +570,7 @@ int chb_depose_scalar(int M, const uint32_t* sort_indx, const double* x, const d
     DepArgs<MM, false> a{sort_indx, x, y, z, nullptr, nullptr, nullptr, nullptr, w, \
                          cell_offset, {}, g, charge, (Nx - 1) * (Nr - 1),       \
                          nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, 0,   \
-                         nullptr, nullptr, nullptr, nullptr};                   \
+                         nullptr, nullptr};                                     \
     for (int k = 0; k < MM + 1; ++k) a.out[k] = rho_host[k];                    \
     return launch_depose<MM, false>(a, st);                                     \
   }
@@ -701,7 +596,7 @@ int chb_depose_vector(int M, const uint32_t* sort_indx, const double* x, const d
     DepArgs<MM, true> a{sort_indx, x, y, z, px, py, pz, g_inv, w, cell_offset,  \
                         {}, g, charge, (Nx - 1) * (Nr - 1),                     \
                         nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, 0,   \
-                        nullptr, nullptr, nullptr, nullptr};                    \
+                        nullptr, nullptr};                                      \
     for (int k = 0; k < 3 * (MM + 1); ++k) a.out[k] = j_host[k];                \
     return launch_depose<MM, true>(a, st);                                      \
   }
@@ -725,10 +620,9 @@ static int push_depose(int M, int push, const uint32_t* sort_indx, double* x, do
                        const double* dt_dev, uint32_t np, int charge, uint32_t Nx, uint32_t Nr,
                        const double* xmin, const double* dx_inv, const double* rmin,
                        const double* dr_inv, double* const* j_host, uint32_t* indx_in_cell,
-                       uint32_t* sum_in_cell, uint32_t* rank_out, unsigned char* dirty,
-                       void* workspace, size_t workspace_bytes, void* stream) {
+                       uint32_t* sum_in_cell, void* workspace, size_t workspace_bytes,
+                       void* stream) {
   if (M < 0 || M >= CHB_MAX_MODES || Nx < 3 || Nr < 3) return CHB_ERR_ARG;
-  if ((rank_out == nullptr) != (dirty == nullptr)) return CHB_ERR_ARG;
   if (np == 0) return CHB_OK;
   if (workspace_bytes < 16 + 8 * sizeof(double) ||
       (reinterpret_cast<uintptr_t>(workspace) & 7u) != 0)
@@ -742,17 +636,12 @@ static int push_depose(int M, int push, const uint32_t* sort_indx, double* x, do
   {
     cudaError_t e = cudaMemsetAsync(exc_count, 0, sizeof(uint32_t), st);
     if (e != cudaSuccess) return (int)e;
-    if (dirty) {                 // one flag per cell and one for the trash bin
-      e = cudaMemsetAsync(dirty, 0, (size_t)(Nx - 1) * (Nr - 1) + 1, st);
-      if (e != cudaSuccess) return (int)e;
-    }
   }
 #define CHB_GO2(MM, PP)                                                         \
   {                                                                             \
     DepArgs<MM, true> a{sort_indx, x, y, z, px, py, pz, g_inv, w, cell_offset,  \
                         {}, g, charge, (Nx - 1) * (Nr - 1), x, y, z, dt_dev, np,  \
-                        exc_count, exc_rec, (uint32_t)cap, indx_in_cell, sum_in_cell, \
-                        rank_out, dirty};                                       \
+                        exc_count, exc_rec, (uint32_t)cap, indx_in_cell, sum_in_cell}; \
     for (int k = 0; k < 3 * (MM + 1); ++k) a.out[k] = j_host[k];                \
     int rc = launch_depose<MM, true, PP>(a, st);                                \
     if (rc) return rc;                                                          \
@@ -779,7 +668,7 @@ int chb_push_depose_vector(int M, const uint32_t* sort_indx, double* x, double* 
                            void* stream) {
   return push_depose(M, 1, sort_indx, x, y, z, px, py, pz, g_inv, w, cell_offset, dt_dev, np,
                      charge, Nx, Nr, xmin, dx_inv, rmin, dr_inv, j_host, nullptr, nullptr,
-                     nullptr, nullptr, workspace, workspace_bytes, stream);
+                     workspace, workspace_bytes, stream);
 }
 
 int chb_push_depose_push_index(int M, const uint32_t* sort_indx, double* x, double* y,
@@ -789,13 +678,12 @@ int chb_push_depose_push_index(int M, const uint32_t* sort_indx, double* x, doub
                                int charge, uint32_t Nx, uint32_t Nr, const double* xmin,
                                const double* dx_inv, const double* rmin, const double* dr_inv,
                                double* const* j_host, uint32_t* indx_in_cell,
-                               uint32_t* sum_in_cell, uint32_t* rank_out,
-                               unsigned char* dirty, void* workspace, size_t workspace_bytes,
+                               uint32_t* sum_in_cell, void* workspace, size_t workspace_bytes,
                                void* stream) {
   if (!indx_in_cell || !sum_in_cell) return CHB_ERR_ARG;
   return push_depose(M, 2, sort_indx, x, y, z, px, py, pz, g_inv, w, cell_offset, dt_dev, np,
                      charge, Nx, Nr, xmin, dx_inv, rmin, dr_inv, j_host, indx_in_cell,
-                     sum_in_cell, rank_out, dirty, workspace, workspace_bytes, stream);
+                     sum_in_cell, workspace, workspace_bytes, stream);
 }
 
 int chb_postproc_depose(double* const* fld_host, const int* is_complex_host, int nfld,

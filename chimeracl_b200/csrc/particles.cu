@@ -402,90 +402,6 @@ sort_fixup_kernel(const uint32_t* __restrict__ cell_offset, uint32_t nbins,
   }
 }
 
-// ------------------------------------------------------------------ incremental re-sort
-// When the previous stable order is known and only a few particles change cell per step
-// (chb_push_depose_push_index leaves rank[] and dirty[], see include/chimera_b200.h):
-// a cell that receives no mover keeps its stayers in their previous relative order, so
-// the slot of a stayer is cell_offset[cell] + rank -- one coalesced pass, no atomics.
-// Only the members of the cells that DO receive movers claim slots atomically and have
-// their segments sorted afterwards (sort_fixup_dirty_kernel).
-constexpr uint32_t kMoverRank = 0xffffffffu;
-
-__global__ void __launch_bounds__(kBlock)
-sort_scatter_incremental_kernel(const uint32_t* __restrict__ indx_in_cell,
-                                const uint32_t* __restrict__ rank,
-                                const unsigned char* __restrict__ dirty,
-                                const uint32_t* __restrict__ cell_offset,
-                                uint32_t* __restrict__ cursor, uint32_t* __restrict__ sort_indx,
-                                uint32_t n) {
-  const uint32_t stride = gridDim.x * kBlock * kIlp;
-  for (uint32_t base = blockIdx.x * kBlock * kIlp + threadIdx.x; base < n; base += stride) {
-    uint32_t cell[kIlp], rk[kIlp], off[kIlp];
-    unsigned char d[kIlp];
-#pragma unroll
-    for (int k = 0; k < kIlp; ++k) {
-      const uint32_t i = base + k * kBlock;
-      if (i < n) { cell[k] = indx_in_cell[i]; rk[k] = rank[i]; }
-    }
-#pragma unroll
-    for (int k = 0; k < kIlp; ++k) {
-      const uint32_t i = base + k * kBlock;
-      if (i < n) { d[k] = __ldg(dirty + cell[k]); off[k] = __ldg(cell_offset + cell[k]); }
-    }
-#pragma unroll
-    for (int k = 0; k < kIlp; ++k) {
-      const uint32_t i = base + k * kBlock;
-      if (i < n) {
-        const uint32_t slot = (rk[k] != kMoverRank && !d[k]) ? off[k] + rk[k]
-                                                             : atomicAdd(&cursor[cell[k]], 1u);
-        sort_indx[slot] = i;
-      }
-    }
-  }
-}
-
-// segments of the dirty cells into ascending storage order (what the serial reference
-// scatter produces); small ones by their own thread in place, larger ones staged and
-// sorted by the CTA, giant ones queued for sort_giant_kernel
-__global__ void __launch_bounds__(kFixBlock)
-sort_fixup_dirty_kernel(const uint32_t* __restrict__ cell_offset,
-                        const unsigned char* __restrict__ dirty, uint32_t nbins,
-                        uint32_t* __restrict__ sort_indx, uint32_t* __restrict__ giant_count,
-                        uint32_t* __restrict__ giant_list, uint32_t giant_cap) {
-  __shared__ uint32_t stage[kFixCapPadded];
-  __shared__ uint32_t big_list[kFixBlock];
-  __shared__ uint32_t big_n;
-  for (uint32_t c0 = blockIdx.x * kFixBlock; c0 < nbins; c0 += gridDim.x * kFixBlock) {
-    const uint32_t c = c0 + threadIdx.x;
-    if (threadIdx.x == 0) big_n = 0;
-    __syncthreads();
-    if (c < nbins && dirty[c]) {
-      const uint32_t s = cell_offset[c], nseg = cell_offset[c + 1] - s;
-      if (nseg > 1) {
-        if (nseg <= (uint32_t)kSmall) insertion_sort(sort_indx + s, (int)nseg);
-        else big_list[atomicAdd(&big_n, 1u)] = threadIdx.x;
-      }
-    }
-    __syncthreads();
-    const uint32_t nb = big_n;
-    for (uint32_t b = 0; b < nb; ++b) {
-      const uint32_t t = big_list[b];
-      const uint32_t bs = cell_offset[c0 + t], bn = cell_offset[c0 + t + 1] - bs;
-      if (bn <= (uint32_t)kFixCap) {
-        for (uint32_t i = threadIdx.x; i < bn; i += kFixBlock) stage[SP(i)] = sort_indx[bs + i];
-        __syncthreads();
-        bitonic_sort_smem(stage, 0, (int)bn);
-        for (uint32_t i = threadIdx.x; i < bn; i += kFixBlock) sort_indx[bs + i] = stage[SP(i)];
-        __syncthreads();
-      } else if (threadIdx.x == 0) {
-        const uint32_t k = atomicAdd(giant_count, 1u);
-        if (k < giant_cap) giant_list[k] = c0 + t;
-      }
-    }
-    __syncthreads();
-  }
-}
-
 // Single-CTA stable LSD radix sort (8-bit digits) of one giant segment, keys =
 // storage indices < 2^key_bits.  Ping-pongs between the segment and `tmp`.
 constexpr int kRadixBlock = 1024;
@@ -669,32 +585,6 @@ int chb_sort_scatter_stable(const uint32_t* indx_in_cell, const uint32_t* cell_o
   int fgrid = stream_grid(nbins, kFixBlock, 8);
   sort_fixup_kernel<<<fgrid, kFixBlock, 0, st>>>(cell_offset, nbins, sort_indx, giant_count,
                                                  giant_list, CHB_GIANT_CAP);
-  int key_bits = 1;
-  while (key_bits < 32 && (1ull << key_bits) < (uint64_t)np) ++key_bits;
-  sort_giant_kernel<<<32, kRadixBlock, 0, st>>>(cell_offset, giant_count, giant_list,
-                                                CHB_GIANT_CAP, sort_indx, tmp, key_bits);
-  CHB_RETURN_LAST_ERROR();
-}
-
-int chb_sort_scatter_incremental(const uint32_t* indx_in_cell, const uint32_t* rank,
-                                 const unsigned char* dirty, const uint32_t* cell_offset,
-                                 uint32_t* cursor, uint32_t* sort_indx, uint32_t np,
-                                 uint32_t nbins, void* workspace, size_t workspace_bytes,
-                                 void* stream) {
-  if (np == 0) return CHB_OK;
-  if (!rank || !dirty) return CHB_ERR_ARG;
-  size_t need = ((size_t)1 + CHB_GIANT_CAP + np) * sizeof(uint32_t);
-  if (workspace_bytes < need) return CHB_ERR_WORKSPACE;
-  cudaStream_t st = (cudaStream_t)stream;
-  uint32_t* giant_count = (uint32_t*)workspace;
-  uint32_t* giant_list = giant_count + 1;
-  uint32_t* tmp = giant_list + CHB_GIANT_CAP;
-  cudaError_t e = cudaMemsetAsync(giant_count, 0, sizeof(uint32_t), st);
-  if (e != cudaSuccess) return (int)e;
-  sort_scatter_incremental_kernel<<<stream_grid(np, kBlock * kIlp, 8), kBlock, 0, st>>>(
-      indx_in_cell, rank, dirty, cell_offset, cursor, sort_indx, np);
-  sort_fixup_dirty_kernel<<<stream_grid(nbins, kFixBlock, 8), kFixBlock, 0, st>>>(
-      cell_offset, dirty, nbins, sort_indx, giant_count, giant_list, CHB_GIANT_CAP);
   int key_bits = 1;
   while (key_bits < 32 && (1ull << key_bits) < (uint64_t)np) ++key_bits;
   sort_giant_kernel<<<32, kRadixBlock, 0, st>>>(cell_offset, giant_count, giant_list,

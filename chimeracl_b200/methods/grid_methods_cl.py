@@ -58,15 +58,12 @@ class GridMethodsCL(GenericMethodsCL):
             # one pass: push, deposit, second push, cell index + histogram
             # (chb_push_depose_push_index); the caller finishes the sort
             indx, hist = parts.prepare_index(self)
-            rank, dirty = parts.prepare_incremental_sort(self)
             self._call('chb_push_depose_push_index', int(self.Args['M']), P['sort_indx'].ptr,
                        P['x'].ptr, P['y'].ptr, P['z'].ptr, P[vec[0]].ptr, P[vec[1]].ptr,
                        P[vec[2]].ptr, P[factors[0]].ptr, P[factors[1]].ptr,
                        P['cell_offset'].ptr, P[push_dt].ptr, int(parts.Args['Np']),
                        int(np.int8(charge)), *self._geom(), _lib.ptr_array(flds),
-                       indx.ptr, hist.ptr, rank.ptr if rank is not None else None,
-                       dirty.ptr if dirty is not None else None,
-                       *parts.exception_workspace())
+                       indx.ptr, hist.ptr, *parts.exception_workspace())
             parts.exception_count_readback()
             parts.flag_sorted = False
             parts._index_prefilled = True

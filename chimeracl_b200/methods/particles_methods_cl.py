@@ -277,20 +277,6 @@ class ParticleMethodsCL(GenericMethodsCL):
         D['sum_in_cell'].t.zero_()
         return D['indx_in_cell'], D['sum_in_cell']
 
-    def prepare_incremental_sort(self, grid):
-        """Workspaces the one-pass particle side fills for the incremental re-sort that
-        follows it (chb_sort_scatter_incremental): per-particle stayer rank and per-cell
-        incomer flag; (None, None) when CHB_INCREMENTAL_SORT=0 (full scatter + fix-up)."""
-        import os
-        self._incremental = None
-        if os.environ.get('CHB_INCREMENTAL_SORT', '1') == '0':
-            return None, None
-        Np = int(self.Args['Np'])
-        nbins = int(grid.Args['Nxm1Nrm1']) + 1
-        self._incremental = (self._buf('stayer_rank', Np, np.uint32),
-                             self._buf('cell_dirty', nbins, np.uint8))
-        return self._incremental
-
     def index_sort(self, grid):
         lib, st = self._lib, self._stream
         D, G = self.DataDev, grid.DataDev
@@ -344,14 +330,6 @@ class ParticleMethodsCL(GenericMethodsCL):
 
         sb = lib.chb_sort_workspace_bytes(Np, nbins)
         sws = self._buf('sort_ws', (sb + 3) // 4, np.uint32)
-        inc = self.__dict__.pop('_incremental', None) if prefilled else None
-        if inc is not None:
-            # the one-pass particle side left the stayer ranks and the incomer flags:
-            # stayers of untouched cells keep their relative order, no atomics, no fix-up
-            _lib.check(lib.chb_sort_scatter_incremental(
-                D['indx_in_cell'].ptr, inc[0].ptr, inc[1].ptr, D['cell_offset'].ptr, cursor.ptr,
-                D['sort_indx'].ptr, Np, nbins, sws.ptr, sb, st), 'chb_sort_scatter_incremental')
-            return
         _lib.check(lib.chb_sort_scatter_stable(D['indx_in_cell'].ptr, D['cell_offset'].ptr,
                                                cursor.ptr, D['sort_indx'].ptr, Np, nbins,
                                                sws.ptr, sb, st), 'chb_sort_scatter_stable')

@@ -140,8 +140,7 @@ int chb_push_depose_vector(int M, const uint32_t* sort_indx, double* x, double* 
  * would use, so x, y, z are bit-identical) and the index_and_sum_in_cell of the second
  * sort_parts: indx_in_cell[np] and sum_in_cell (zeroed by the caller, (Nx-1)*(Nr-1)+1
  * bins) are those chb_push_index would produce.  The caller continues with
- * chb_cell_offsets and chb_sort_scatter_stable (or, having passed rank_out / dirty,
- * chb_sort_scatter_incremental). */
+ * chb_cell_offsets and chb_sort_scatter_stable. */
 int chb_push_depose_push_index(int M, const uint32_t* sort_indx, double* x, double* y,
                                double* z, const double* px, const double* py,
                                const double* pz, const double* g_inv, const double* w,
@@ -149,25 +148,8 @@ int chb_push_depose_push_index(int M, const uint32_t* sort_indx, double* x, doub
                                int charge, uint32_t Nx, uint32_t Nr, const double* xmin,
                                const double* dx_inv, const double* rmin, const double* dr_inv,
                                double* const* j_host, uint32_t* indx_in_cell,
-                               uint32_t* sum_in_cell, uint32_t* rank_out,
-                               unsigned char* dirty, void* workspace, size_t workspace_bytes,
+                               uint32_t* sum_in_cell, void* workspace, size_t workspace_bytes,
                                void* stream);
-
-/* Incremental form of chb_sort_scatter_stable (same reference stage, index_sort's `sort`
- * launch, particles_methods_cl.py:252-261 -> particles_generic.cl:186-201; same result,
- * the stable permutation).  chb_push_depose_push_index, given rank_out[np] and
- * dirty[(Nx-1)*(Nr-1)+1] (both or neither; it zeroes dirty itself), records for every
- * particle its rank among the particles of its previous cell that STAY there (or
- * 0xffffffff if it changes cell) and flags every cell a particle moves INTO.  A cell
- * without incomers keeps its stayers in their previous relative order, so their slots
- * are cell_offset[cell] + rank: one coalesced pass without atomics; only the members of
- * flagged cells claim slots atomically and are sorted afterwards.  cursor / workspace as
- * for chb_sort_scatter_stable. */
-int chb_sort_scatter_incremental(const uint32_t* indx_in_cell, const uint32_t* rank,
-                                 const unsigned char* dirty, const uint32_t* cell_offset,
-                                 uint32_t* cursor, uint32_t* sort_indx, uint32_t np,
-                                 uint32_t nbins, void* workspace, size_t workspace_bytes,
-                                 void* stream);
 
 /* row1 -= row0, then arr[ir,:] *= dV_inv[ir], for nfld arrays in one launch
  * (is_complex_host[k] != 0 for complex arrays).  Replaces treat_axis_{d,c} and

@@ -161,53 +161,14 @@ class EmulatedLib:
 
     def chb_push_depose_push_index(self, M, sort_indx, x, y, z, px, py, pz, g_inv, w,
                                    cell_offset, dt, n, charge, Nx, Nr, xmin, dx_inv, rmin,
-                                   dr_inv, j, indx, summ, rank, dirty, ws, wsb, stream):
+                                   dr_inv, j, indx, summ, ws, wsb, stream):
         g, v = self._push_depose(M, x, y, z, px, py, pz, g_inv, w, dt, n, charge, Nx, Nr,
                                  (xmin, dx_inv, rmin, dr_inv), j)
         K = self._kern(M)
         K.push_xyz(*v[:7], float(_vec(dt, 1, F8)[0]))
         i, s = K.index_and_sum(v[0], v[1], v[2], g)
         _vec(indx, n, np.uint32)[...] = i
-        nbins = g["Nxm1Nrm1"] + 1
-        _vec(summ, nbins, np.uint32)[...] += s
-        if rank:
-            # the contract of include/chimera_b200.h: rank among the stayers of the
-            # previous cell (previous stable order), 0xffffffff for cell changers, and a
-            # flag on every cell that receives one (old trash-bin particles count as movers)
-            order = _vec(sort_indx, n, np.uint32).astype(np.int64)
-            offs = _vec(cell_offset, nbins + 1, np.uint32).astype(np.int64)
-            old_cell = np.empty(n, np.int64)
-            old_cell[order] = np.repeat(np.arange(nbins), np.diff(offs))
-            stay = (i.astype(np.int64) == old_cell) & (old_cell < nbins - 1)
-            st_sorted = stay[order].astype(np.int64)
-            before = np.cumsum(st_sorted) - st_sorted          # stayers before, global
-            cell_sorted = old_cell[order]
-            first = offs[cell_sorted]                          # start of the old cell
-            r = before - before[np.minimum(first, n - 1)]
-            rk = np.full(n, 0xffffffff, np.uint32)
-            rk[order[st_sorted == 1]] = r[st_sorted == 1].astype(np.uint32)
-            _vec(rank, n, np.uint32)[...] = rk
-            d = _vec(dirty, nbins, np.uint8)
-            d[...] = 0
-            d[i[~stay]] = 1
-        return 0
-
-    def chb_sort_scatter_incremental(self, indx, rank, dirty, cell_offset, cursor, sort_indx, n,
-                                     nbins, ws, wsb, stream):
-        idx = _vec(indx, n, np.uint32).astype(np.int64)
-        rk = _vec(rank, n, np.uint32)
-        d = _vec(dirty, nbins, np.uint8)
-        offs = _vec(cell_offset, nbins + 1, np.uint32).astype(np.int64)
-        out = _vec(sort_indx, n, np.uint32)
-        fast = (rk != 0xffffffff) & (d[idx] == 0)
-        out[offs[idx[fast]] + rk[fast].astype(np.int64)] = np.flatnonzero(fast)
-        slow = np.flatnonzero(~fast)                           # ascending storage index
-        srt = slow[np.argsort(idx[slow], kind="stable")]
-        cells, cnt = np.unique(idx[srt], return_counts=True)
-        assert (np.diff(offs)[cells] == cnt).all(), "a flagged cell has unflagged members"
-        pos = np.concatenate([offs[c] + np.arange(k) for c, k in zip(cells, cnt)]) \
-            if cells.size else np.empty(0, np.int64)
-        out[pos] = srt
+        _vec(summ, g["Nxm1Nrm1"] + 1, np.uint32)[...] += s
         return 0
 
     def chb_postproc_depose(self, flds, is_complex, nfld, Nx, Nr, dV_inv, stream):
