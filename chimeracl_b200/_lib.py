@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libchimera_b200.so")
+LIB_PATH = os.environ.get("CHB_LIB") or os.path.join(_HERE, "libchimera_b200.so")
 
 _vp, _u32, _i32, _sz, _dbl = (ctypes.c_void_p, ctypes.c_uint32, ctypes.c_int,
                               ctypes.c_size_t, ctypes.c_double)

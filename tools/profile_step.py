@@ -15,6 +15,8 @@ def main():
     ap.add_argument("--presteps", type=int, default=30,
                     help="unprofiled steps first: the lattice start (16 per cell exactly, nobody "
                          "changes cell for ~25 steps) is not the steady state")
+    ap.add_argument("--time", action="store_true",
+                    help="no profiler: CUDA-event time of every C-ABI call and of the step")
     a = ap.parse_args()
     import torch
     from chimeracl_b200.methods.generic_methods_cl import Communicator
@@ -36,6 +38,23 @@ def main():
     for _ in range(max(1, a.presteps)):   # (the first step cannot use the one-pass particle side)
         loop.step()
     torch.cuda.synchronize()
+    if a.time:
+        from chimeracl_b200 import _lib
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(a.steps):
+            loop.step()
+        e1.record()
+        torch.cuda.synchronize()
+        print("step %.3f ms" % (e0.elapsed_time(e1) / a.steps))
+        lib = _lib.load()
+        lib.enable_profiling()
+        for _ in range(a.steps):
+            loop.step()
+        rep = lib.profile_report()
+        for k, (n, t) in sorted(rep.items(), key=lambda kv: -kv[1][1]):
+            print("  %-32s %5.1f calls/step %8.3f ms/step" % (k, n / a.steps, t / a.steps))
+        return
     torch.cuda.profiler.start()
     for _ in range(a.steps):
         loop.step()
