@@ -17,7 +17,7 @@ loop_steps = ['frame', 'push-x', 'sort', 'depose',
 
 class PIC_loop:
     def __init__(self, solvers=[], species=[], frames=[], diags=[], timit=False,
-                 fuse_push_sort=True, real_m0_symmetry=True):
+                 fuse_push_sort=True, real_m0_symmetry=True, align_every=None):
         self.solvers = solvers
         self.mainsolver = self.solvers[0]
         self.species = species
@@ -27,6 +27,14 @@ class PIC_loop:
         self.it = 0
         self.fuse_push_sort = bool(fuse_push_sort)
         self.real_m0_symmetry = bool(real_m0_symmetry)
+        # align_every=N: every N steps the loop calls species.align_parts() itself (the
+        # reference API call, particles.py:42-51, which the reference only issues on plasma
+        # injection, frame.py:59).  Between aligns the storage order drifts away from the
+        # cell order and every kernel that visits particles through sort_indx loses
+        # coalescing (cfg3: one-pass particle kernel 1.3 -> 1.9 ms 40 steps after an align).
+        # Opt-in, because align_parts() reorders the DataDev arrays and drops the
+        # particles of the trash bin, as it does in the reference.
+        self.align_every = int(align_every) if align_every else 0
         if self.timit is True:
             self.Timer = {key: 0 for key in loop_steps}
             self._events = []
@@ -61,6 +69,12 @@ class PIC_loop:
             if np.mod(self.it, frame.Args['Steps']) == 0:
                 frame.shift_grids(grids=self.solvers)
                 frame.inject_plasma(species=self.species, grid=self.mainsolver)
+        if self.align_every and self.it > 0 and self.it % self.align_every == 0:
+            for parts in self.species:
+                if 'Immobile' in parts.Args.keys():
+                    continue
+                parts.sort_parts(grid=self.mainsolver)
+                parts.align_parts()
         self.timer_record('frame')
 
         # first half push + sort + current deposit.  When every mobile species still

@@ -15,6 +15,7 @@ def main():
     ap.add_argument("--presteps", type=int, default=30,
                     help="unprofiled steps first: the lattice start (16 per cell exactly, nobody "
                          "changes cell for ~25 steps) is not the steady state")
+    ap.add_argument("--align-every", type=int, default=0)
     ap.add_argument("--time", action="store_true",
                     help="no profiler: CUDA-event time of every C-ABI call and of the step")
     a = ap.parse_args()
@@ -34,7 +35,7 @@ def main():
     for p in (eons, ions):
         p.sort_parts(solver)
         p.align_parts()
-    loop = PIC_loop(solvers=[solver], species=[eons, ions])
+    loop = PIC_loop(solvers=[solver], species=[eons, ions], align_every=a.align_every)
     for _ in range(max(1, a.presteps)):   # (the first step cannot use the one-pass particle side)
         loop.step()
     torch.cuda.synchronize()
