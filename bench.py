@@ -744,6 +744,26 @@ def run_other_config(args):
         loop.step()
     e1.record()
     torch.cuda.synchronize()
+    # the same steps replayed from CUDA graphs (PIC_loop(use_cuda_graph=True); single rank):
+    # these configurations are launch-bound, the timed steps include the eager steps and
+    # the re-capture every plasma injection forces
+    graph = None
+    if world == 1:
+        loop.use_cuda_graph = True
+        for _ in range(4):
+            loop.step()
+        torch.cuda.synchronize()
+        r0 = loop.graph_replays
+        g0, g1 = ev(), ev()
+        g0.record()
+        for _ in range(args.steps):
+            loop.step()
+        g1.record()
+        torch.cuda.synchronize()
+        graph = {"ms_per_step": g0.elapsed_time(g1) / args.steps,
+                 "replayed_steps": loop.graph_replays - r0, "of_steps": args.steps,
+                 "captures_total": loop.graph_captures}
+        loop.use_cuda_graph = False
     t = torch.tensor([e0.elapsed_time(e1) / args.steps, float(eons.Args["Np"])],
                      dtype=torch.float64, device=comm.device)
     if world > 1:
@@ -763,7 +783,8 @@ def run_other_config(args):
               "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
               "vs_baseline": None, "dtype": "f64", "data": "synthetic",
               "config": {"workload": what, "mobile_particles_total": n_all,
-                         "steps_before_timing": nwarm}, "fields_finite": finite})
+                         "steps_before_timing": nwarm}, "fields_finite": finite,
+              "cuda_graph": graph})
 
 
 def emit(line):

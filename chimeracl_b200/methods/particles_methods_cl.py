@@ -51,6 +51,36 @@ class ParticleMethodsCL(GenericMethodsCL):
                 and 'sort_indx' in self.DataDev
                 and self.DataDev['sort_indx'].size == self.Args['Np'])
 
+    def graph_safe(self, grid):
+        """True if this species' part of a PIC step may be captured in a CUDA graph: no
+        host read-back that a later step has to wait for (the bounded cell-changer queue
+        of very large species), sorted once if immobile."""
+        Np = int(self.Args['Np'])
+        if Np == 0:
+            return True
+        if 'Immobile' in self.Args.keys():
+            return bool(self.flag_sorted)
+        full = int(self._lib.chb_push_depose_workspace_bytes(Np))
+        limit = getattr(self, '_exc_full_limit', None)
+        if limit is None:
+            limit = getattr(self.comm, 'device_memory_bytes', 16 << 30) // 4
+        return full <= limit and getattr(self, '_exc_check', None) is None
+
+    def after_graph_replay(self):
+        """Host-side effect of a replayed step: Args['Np_stay'] resolves to the value the
+        replayed scan copied to pinned memory."""
+        if self.Args['Np'] == 0 or 'Immobile' in self.Args.keys() or \
+                getattr(self, '_np_stay_host', None) is None:
+            return
+        host = self._np_stay_host
+        ev = torch.cuda.Event()
+        ev.record()
+
+        def _resolve():
+            ev.synchronize()
+            return int(host.item())
+        self.Args.set_lazy('Np_stay', _resolve)
+
     def exception_workspace(self):
         """(pointer, bytes) of the scratch chb_push_depose_vector / _push_index need: the
         queue of the particles that changed cell.  Sized for the worst case (one 64-byte

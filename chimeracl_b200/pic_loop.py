@@ -17,7 +17,8 @@ loop_steps = ['frame', 'push-x', 'sort', 'depose',
 
 class PIC_loop:
     def __init__(self, solvers=[], species=[], frames=[], diags=[], timit=False,
-                 fuse_push_sort=True, real_m0_symmetry=True, align_every=None):
+                 fuse_push_sort=True, real_m0_symmetry=True, align_every=None,
+                 use_cuda_graph=False):
         self.solvers = solvers
         self.mainsolver = self.solvers[0]
         self.species = species
@@ -35,6 +36,10 @@ class PIC_loop:
         # Opt-in, because align_parts() reorders the DataDev arrays and drops the
         # particles of the trash bin, as it does in the reference.
         self.align_every = int(align_every) if align_every else 0
+        self.use_cuda_graph = bool(use_cuda_graph)
+        self._graph = None
+        self.graph_captures = 0
+        self.graph_replays = 0
         if self.timit is True:
             self.Timer = {key: 0 for key in loop_steps}
             self._events = []
@@ -77,6 +82,21 @@ class PIC_loop:
                 parts.align_parts()
         self.timer_record('frame')
 
+        if self.use_cuda_graph and self._graph_eligible():
+            self._step_graphed()
+        else:
+            self._graph = None
+            self._step_body()
+
+        for parts in self.species:
+            parts.free_mp()
+
+        self.it += 1
+        return self.it
+
+    def _step_body(self):
+        """One step without the frame / diagnostics / align prologue: only enqueues device
+        work (what a CUDA graph of the step captures)."""
         # first half push + sort + current deposit.  When every mobile species still
         # has the previous step's sort as a valid traversal order, the three are ONE
         # pass and the first sort of the step is not needed; the same pass applies the
@@ -177,11 +197,81 @@ class PIC_loop:
             solver.gather_and_push(species=self.species)
             self.timer_record('gather + push-p')
 
-        for parts in self.species:
-            parts.free_mp()
 
-        self.it += 1
-        return self.it
+    # ---- CUDA-graph replay of the step (small configurations are launch-bound: a step
+    # is ~60 kernel launches issued from Python; cfg1 / cfg4 spend more time enqueueing
+    # than computing).  PIC_loop(use_cuda_graph=True) captures the device work of two
+    # consecutive steps (the dN0 <-> dN1 buffer swap has period 2) and replays them
+    # alternately as long as nothing the captured launches depend on changes: particle
+    # counts, array addresses, Xmin (moving window).  An injection / align / window shift
+    # changes those: that step runs eagerly, the next one re-captures.
+    def _graph_eligible(self):
+        if len(self.solvers) != 1 or self.timit is True or not self.fuse_push_sort:
+            return False
+        if getattr(self, 'on_coordinates_final', None) is not None:
+            return False
+        solver = self.mainsolver
+        if getattr(solver.comm, 'process_group', None) is not None:
+            return False
+        if not hasattr(solver, 'finish_currents'):
+            return False
+        for parts in self.species:
+            if not hasattr(parts, 'graph_safe') or not parts.graph_safe(solver):
+                return False
+        return self._can_fuse_first_half()
+
+    def _graph_signature(self):
+        solver = self.mainsolver
+        sig = [float(solver.Args['Xmin']), int(solver.Args['Nx']), int(solver.Args['Nr'])]
+        for parts in self.species:
+            D = parts.DataDev
+            sig += [int(parts.Args['Np'])] + [D[k].ptr for k in ('x', 'w', 'sort_indx', 'cell_offset')
+                                              if k in D and D[k] is not None]
+        return tuple(sig)
+
+    def _dn_swap(self):
+        solver = self.mainsolver
+        for m in range(0, solver.Args['M'] + 1):
+            for comp in solver.Args['vec_comps']:
+                key = comp + '_fb_m' + str(m)
+                solver.DataDev['dN0' + key], solver.DataDev['dN1' + key] = \
+                    solver.DataDev['dN1' + key], solver.DataDev['dN0' + key]
+
+    def _dn_ptr(self):
+        solver = self.mainsolver
+        return solver.DataDev['dN0' + solver.Args['vec_comps'][0] + '_fb_m0'].ptr
+
+    def _step_graphed(self):
+        sig = self._graph_signature()
+        G = self._graph
+        if G is not None and G['sig'] == sig and self._dn_ptr() in G['dn_ptr']:
+            phase = G['dn_ptr'].index(self._dn_ptr())
+            G['graphs'][phase].replay()
+            self._dn_swap()                       # host-side effects of the captured step
+            for parts in self.species:
+                if hasattr(parts, 'after_graph_replay'):
+                    parts.after_graph_replay()
+            self.graph_replays += 1
+            return
+        if G is None or G.get('pending') != sig:
+            # something changed (or first use): this step runs eagerly -- it also brings
+            # every persistent workspace to its final size -- and the next one captures
+            self._step_body()
+            self._graph = {'sig': None, 'pending': self._graph_signature()}
+            return
+        graphs, ptrs = [], []
+        torch.cuda.synchronize()
+        pool = None
+        for _ in range(2):
+            g = torch.cuda.CUDAGraph()
+            ptrs.append(self._dn_ptr())
+            with torch.cuda.graph(g, pool=pool):
+                self._step_body()
+            pool = g.pool()
+            graphs.append(g)
+        self._graph = {'sig': sig, 'graphs': graphs, 'dn_ptr': ptrs}
+        self.graph_captures += 1
+        self._step_graphed()
 
     def _deposit_and_solve_sharded(self, solver):
         """Charge deposit + field solve of one step with the kr-row sharded spectral solve

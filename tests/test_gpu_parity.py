@@ -961,3 +961,65 @@ def test_cpu_binding_is_best_effort(comm):
         assert len(os.sched_getaffinity(0)) >= 1
     finally:
         os.sched_setaffinity(0, before)
+
+
+# ----------------------------------------------------------------------------- CUDA graph
+def test_cuda_graph_replay_matches_eager(comm):
+    """PIC_loop(use_cuda_graph=True): two captured steps replayed alternately (the dN0/dN1
+    swap has period 2) give what eager steps give -- compared after 7 steps (odd: both
+    captured graphs and the host-side swap bookkeeping are exercised) on the golden case,
+    and against the oracle.  Tolerance 1e-10 (the full-step tolerance: deposit REDs are
+    unordered in both runs)."""
+    from chimeracl_b200.pic_loop import PIC_loop
+    G = load_golden(1)
+    runs = []
+    for graph in (False, True):
+        S, P, I = gpu_case_from_golden(G, comm)
+        loop = PIC_loop(solvers=[S], species=[P, I], use_cuda_graph=graph)
+        for _ in range(7):
+            loop.step()
+        comm.synchronize()
+        runs.append((S, P, loop))
+    (S0, P0, _), (S1, P1, loop1) = runs
+    assert loop1.graph_captures == 1 and loop1.graph_replays == 5   # steps 0, 1 ran eagerly
+    assert int(P1.Args["Np_stay"]) == int(P0.Args["Np_stay"])
+    assert np.array_equal(P1.DataDev["sort_indx"].get(), P0.DataDev["sort_indx"].get())
+    for k in ("Ex_m0", "Ez_m1", "Bz_m1", "rho_m0", "Jx_m1", "Ex_fb_m1", "dN0Jx_fb_m1", "dN1Jx_fb_m0"):
+        assert rel_err(S1.DataDev[k].get(), S0.DataDev[k].get()) < 1e-10, k
+    for k in ("x", "y", "z", "px", "py", "pz", "g_inv"):
+        assert rel_err(P1.DataDev[k].get(), P0.DataDev[k].get()) < 1e-10, k
+    So, Po, Io = oracle_case_from_golden(G, NumpyKernels(1))
+    for _ in range(7):
+        O.pic_step(So, [Po, Io])
+    for k in ("Ex_m0", "Bz_m1", "rho_m0"):
+        assert rel_err(S1.DataDev[k].get(), So.D[k]) < 1e-9, k
+
+
+def test_cuda_graph_with_moving_window(comm):
+    """Graph replay across plasma injections (reduced lpa_script_small, injections at steps
+    0, 20, 40): every injection changes particle counts and array addresses, so that step
+    and the next run eagerly and the pair of graphs is re-captured."""
+    import importlib.util
+    import os
+    from chimeracl_b200.methods.generic_methods_cl import Communicator
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                        "examples", "lpa_script_small.py")
+    spec = importlib.util.spec_from_file_location("lpa_small_g", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    res = []
+    for graph in (False, True):
+        c = Communicator(answers=[0, 0], seed=11)     # same theta draws in both runs
+        _, solver, eons, ions, frame, loop = mod.build(Nx=300, Nr=48, M=1, comm=c)
+        loop.use_cuda_graph = graph
+        for _ in range(45):
+            loop.step()
+        c.synchronize()
+        res.append((solver, eons, loop))
+    (s0, e0, _), (s1, e1, l1) = res
+    assert l1.graph_captures == 3 and l1.graph_replays == 45 - 3 * 2
+    assert int(e1.Args["Np"]) == int(e0.Args["Np"])
+    for k in ("Ez_m0", "Ex_m1", "Bz_m1", "rho_m0"):
+        assert rel_err(s1.DataDev[k].get(), s0.DataDev[k].get()) < 1e-9, k
+    for k in ("x", "px", "g_inv"):
+        assert rel_err(e1.DataDev[k].get(), e0.DataDev[k].get()) < 1e-9, k
