@@ -38,6 +38,9 @@ class PIC_loop:
         self.align_every = int(align_every) if align_every else 0
         self.use_cuda_graph = bool(use_cuda_graph)
         self._graph = None
+        self._graph_pool = None
+        self._graph_stream = None
+        self._graph_keep = None
         self.graph_captures = 0
         self.graph_replays = 0
         if self.timit is True:
@@ -260,15 +263,30 @@ class PIC_loop:
             self._graph = {'sig': None, 'pending': self._graph_signature()}
             return
         graphs, ptrs = [], []
-        torch.cuda.synchronize()
-        pool = None
-        for _ in range(2):
-            g = torch.cuda.CUDAGraph()
-            ptrs.append(self._dn_ptr())
-            with torch.cuda.graph(g, pool=pool):
-                self._step_body()
-            pool = g.pool()
-            graphs.append(g)
+        # low-level capture (torch.cuda.graph() would run gc.collect() and empty_cache()
+        # on every re-capture, i.e. after every plasma injection): a side stream ordered
+        # after the work already enqueued, one private memory pool for the loop's lifetime
+        # (the previous pair of graphs is kept alive until the new one exists, so that the
+        # pool -- released with its last graph -- can be shared)
+        old = self._graph_keep
+        if self._graph_stream is None:
+            self._graph_stream = torch.cuda.Stream()
+        self._graph_pool = old[0].pool() if old else torch.cuda.graph_pool_handle()
+        cur = torch.cuda.current_stream()
+        side = self._graph_stream
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                g = torch.cuda.CUDAGraph()
+                ptrs.append(self._dn_ptr())
+                g.capture_begin(pool=self._graph_pool, capture_error_mode="thread_local")
+                try:
+                    self._step_body()
+                finally:
+                    g.capture_end()
+                graphs.append(g)
+        cur.wait_stream(side)
+        self._graph_keep = graphs
         self._graph = {'sig': sig, 'graphs': graphs, 'dn_ptr': ptrs}
         self.graph_captures += 1
         self._step_graphed()

@@ -984,7 +984,7 @@ def test_cuda_graph_replay_matches_eager(comm):
     assert loop1.graph_captures == 1 and loop1.graph_replays == 5   # steps 0, 1 ran eagerly
     assert int(P1.Args["Np_stay"]) == int(P0.Args["Np_stay"])
     assert np.array_equal(P1.DataDev["sort_indx"].get(), P0.DataDev["sort_indx"].get())
-    for k in ("Ex_m0", "Ez_m1", "Bz_m1", "rho_m0", "Jx_m1", "Ex_fb_m1", "dN0Jx_fb_m1", "dN1Jx_fb_m0"):
+    for k in ("Ex_m0", "Ez_m1", "Bz_m1", "rho_m0", "Jx_m1", "Ex_fb_m1", "dN0x_fb_m1", "dN1x_fb_m0"):
         assert rel_err(S1.DataDev[k].get(), S0.DataDev[k].get()) < 1e-10, k
     for k in ("x", "y", "z", "px", "py", "pz", "g_inv"):
         assert rel_err(P1.DataDev[k].get(), P0.DataDev[k].get()) < 1e-10, k
@@ -1017,9 +1017,17 @@ def test_cuda_graph_with_moving_window(comm):
         c.synchronize()
         res.append((solver, eons, loop))
     (s0, e0, _), (s1, e1, l1) = res
-    assert l1.graph_captures == 3 and l1.graph_replays == 45 - 3 * 2
+    assert l1.graph_captures == 3 and l1.graph_replays == 45 - 3
     assert int(e1.Args["Np"]) == int(e0.Args["Np"])
-    for k in ("Ez_m0", "Ex_m1", "Bz_m1", "rho_m0"):
-        assert rel_err(s1.DataDev[k].get(), s0.DataDev[k].get()) < 1e-9, k
-    for k in ("x", "px", "g_inv"):
-        assert rel_err(e1.DataDev[k].get(), e0.DataDev[k].get()) < 1e-9, k
+    # scale: the laser field (rho and the m = 1 longitudinal fields are rounding noise while
+    # the plasma that has entered still has ~zero weight, so their own maximum is no scale)
+    names = [c + a + m for c in "EB" for a in "xyz" for m in ("_m0", "_m1")]
+    scale = max(float(np.abs(s0.DataDev[k].get()).max()) for k in names)
+    assert scale > 1.0
+    for k in names:
+        d = np.abs(s1.DataDev[k].get() - s0.DataDev[k].get()).max()
+        assert d / scale < 1e-10, (k, d / scale)
+    assert np.array_equal(e1.DataDev["x"].get(), e0.DataDev["x"].get())
+    # momenta of near-axis particles amplify the rounding noise of the m = 1 fields (1/r)
+    for k in ("px", "py", "pz", "g_inv"):
+        assert rel_err(e1.DataDev[k].get(), e0.DataDev[k].get()) < 1e-6, k
