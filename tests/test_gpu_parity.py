@@ -997,7 +997,7 @@ def test_cuda_graph_replay_matches_eager(comm):
 
 def test_cuda_graph_with_moving_window(comm):
     """Graph replay across plasma injections (reduced lpa_script_small, injections at steps
-    0, 20, 40): every injection changes particle counts and array addresses, so that step
+    0, 20, ..., 120): every injection changes particle counts and array addresses, so that step
     and the next run eagerly and the pair of graphs is re-captured."""
     import importlib.util
     import os
@@ -1012,12 +1012,15 @@ def test_cuda_graph_with_moving_window(comm):
         c = Communicator(answers=[0, 0], seed=11)     # same theta draws in both runs
         _, solver, eons, ions, frame, loop = mod.build(Nx=300, Nr=48, M=1, comm=c)
         loop.use_cuda_graph = graph
-        for _ in range(45):
+        # 140 steps: the plasma has reached the laser; later this reduced run amplifies
+        # rounding noise by ~100x per 10 steps (two eager runs diverge the same way:
+        # tools/graph_lockstep.py with BOTH_EAGER=1)
+        for _ in range(140):
             loop.step()
         c.synchronize()
         res.append((solver, eons, loop))
     (s0, e0, _), (s1, e1, l1) = res
-    assert l1.graph_captures == 3 and l1.graph_replays == 45 - 3
+    assert l1.graph_captures == 7 and l1.graph_replays == 140 - 7
     assert int(e1.Args["Np"]) == int(e0.Args["Np"])
     # scale: the laser field (rho and the m = 1 longitudinal fields are rounding noise while
     # the plasma that has entered still has ~zero weight, so their own maximum is no scale)
@@ -1026,8 +1029,8 @@ def test_cuda_graph_with_moving_window(comm):
     assert scale > 1.0
     for k in names:
         d = np.abs(s1.DataDev[k].get() - s0.DataDev[k].get()).max()
-        assert d / scale < 1e-10, (k, d / scale)
-    assert np.array_equal(e1.DataDev["x"].get(), e0.DataDev["x"].get())
+        assert d / scale < 1e-8, (k, d / scale)
+    assert rel_err(e1.DataDev["x"].get(), e0.DataDev["x"].get()) < 1e-9
     # momenta of near-axis particles amplify the rounding noise of the m = 1 fields (1/r)
     for k in ("px", "py", "pz", "g_inv"):
         assert rel_err(e1.DataDev[k].get(), e0.DataDev[k].get()) < 1e-6, k
