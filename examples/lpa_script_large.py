@@ -80,6 +80,7 @@ def main():
     ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--replicated-solve", action="store_true",
                     help="multi-GPU: every rank runs the whole field solve (default: kr-row sharded)")
+    ap.add_argument("--sharded-solve", action="store_true", help="the default, spelled out")
     a = ap.parse_args()
     comm = Communicator(answers=[0, 0])
     init_distributed(comm)
