@@ -107,6 +107,31 @@ class ArgsDict(dict):
     def get(self, key, default=None):
         return self[key] if key in self else default
 
+    # every other read path resolves pending values too, so that a _Lazy never leaks
+    def __iter__(self):            # (own tp_iter: dict(Args) then goes through __getitem__)
+        return dict.__iter__(self)
+
+    def _resolve_all(self):
+        for key in [k for k, v in dict.items(self) if isinstance(v, _Lazy)]:
+            self[key]
+
+    def items(self):
+        self._resolve_all()
+        return dict.items(self)
+
+    def values(self):
+        self._resolve_all()
+        return dict.values(self)
+
+    def copy(self):
+        self._resolve_all()
+        return ArgsDict(dict.copy(self))
+
+    def pop(self, key, *default):
+        if key in self:
+            self[key]
+        return dict.pop(self, key, *default)
+
 
 class _Lazy:
     __slots__ = ("fn",)

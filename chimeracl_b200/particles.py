@@ -45,8 +45,10 @@ class Particles(ParticleMethodsCL):
         self.align_and_damp(comps_align=comps)
 
     def _process_configs(self, configs_in):
-        """Defaults and derived constants of reference particles.py:53-100; the
-        caller's dict is filled in place, as the reference does."""
+        """Defaults and derived constants of reference particles.py:53-100.  The reference
+        keeps the caller's dict itself as Args; here Args is an ArgsDict (lazy Np_stay)
+        built from it, and the derived keys are written back into the caller's dict once --
+        later changes (Np, right_lim, InjectorSource) are visible through parts.Args only."""
         A = ArgsDict(configs_in)
         self._user_configs = configs_in
         A['Np'] = 0

@@ -75,7 +75,8 @@ class SpectralSharding:
         R = spectral_rows(K, 0, world)[2]
         self._sharding = {'world': world, 'rank': rank, 'emulate': bool(emulate), 'R': R,
                           'stores': {}}
-        # CHB_PEER_EXCHANGE=1 | multimem (opt-in, not yet run on hardware): the exchanged
+        # CHB_PEER_EXCHANGE=1 | multimem (opt-in; run on 2 and 8 B200 in round 2, parity
+        # 1.5e-14 / 8.4e-14 against the replicated solve, profiles/README.md): the exchanged
         # buffers are symmetric memory and the exchanges are own kernels over NVLink peer
         # memory (csrc/peer.cu: P2P loads / stores, or NVSwitch multimem) between cross-rank
         # barriers of the symmetric-memory handles, instead of NCCL collectives
@@ -162,6 +163,12 @@ class SpectralSharding:
             # ahead of it
             chunk = st['R'] * int(self.Args['Nx']) * 2
             own = (self._shard.hi - self._shard.lo) * int(self.Args['Nx']) * 2
+            # write-after-read: no rank may still be contracting with the previous contents
+            # of these arrays when the new rows land in them.  Inside PIC_loop the barriers
+            # of the previous reduce_grid_fields() already order that, a direct caller
+            # (Diagnostics, restore_B_fb(gathered=False)) has no such guarantee: one cheap
+            # cross-rank barrier before the push makes it unconditional
+            st['peer'][keys[0]][0].barrier(channel=2)
             for key in keys:
                 _, ptrs, mc = st['peer'][key]
                 self._call('chb_peer_allgather_f64', ptrs, st['world'], st['rank'], mc,

@@ -3,7 +3,7 @@
 # (round 1 covered N = 2 and 4; N = 8 and cfg5 are open).  Everything lands in gpurun_out/.
 # SECTIONS="parity bench variants peer cfg5" (default: all) picks what runs; TAG prefixes the outputs.
 N=${1:-8}
-SECTIONS=${SECTIONS:-parity replicated bench weak variants peer cfg5}
+SECTIONS=${SECTIONS:-parity replicated bench weak variants tile128 peer cfg5}
 has() { case " $SECTIONS " in *" $1 "*) return 0;; esac; return 1; }
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
@@ -29,7 +29,7 @@ has replicated && bench replicated "A=0" "--replicated-solve"
 has bench && bench sharded "A=0" ""
 has weak && bench sharded_weak "A=0" "--scaling weak"
 has variants && bench sharded_hiprio "TORCH_NCCL_HIGH_PRIORITY=1" ""
-has variants && bench sharded_tile128 "CHB_DHT_TILE64=0" ""
+has tile128 && bench sharded_tile128 "CHB_DHT_TILE64=0" ""
 
 # 2b. E/B partial sums through own kernels over peer memory instead of NCCL (compiled, never
 #     run before): parity first, then the bench, P2P and NVSwitch-multicast flavours
