@@ -38,7 +38,10 @@ namespace chb {
 #endif
 constexpr int kGatCells = CHB_GAT_CELLS;      // max cells per tile
 constexpr int kGatCols = kGatCells + 1;
-constexpr int kGatThreads = 512;
+#ifndef CHB_GAT_THREADS
+#define CHB_GAT_THREADS 512
+#endif
+constexpr int kGatThreads = CHB_GAT_THREADS;
 constexpr int kGatCtasPerSm = 1;              // persistent CTAs per SM (2 x 256 threads measured slower)
 constexpr int kGatSlots = CHB_GAT_SLOTS;      // pipelined particles per thread and tile
 constexpr int kGatRound = kGatSlots * kGatThreads;
