@@ -371,14 +371,19 @@ static cudaError_t launch_wide(const GemmArgs& p, int nbatch, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-// 64-row tiles: width 32*nt columns, nt = 4..7 (nt = 8 would not fit the shared memory)
+// 64-row tiles: width 32*nt columns, nt = 2..7 (nt = 8 would not fit the shared memory).
+// Narrow tiles (nt = 2, 3) exist for the single right-hand sides of an 8-way sharded solve:
+// a 64 x 8192 result is 37-64 tiles with nt >= 4, i.e. a quarter to a half of the 148 SMs;
+// their fragment-load : DMMA ratio is worse ((2 + nt) / 2nt: 1.0, 0.83 against 0.64 at
+// nt = 7), which the cost accounts for.
 static int pick_wide64_nt(uint32_t N, int nbatch) {
   int best = 0;
   double best_cost = 0;
-  for (int nt = 4; nt <= 7; ++nt) {
+  for (int nt = 2; nt <= 7; ++nt) {
     const uint64_t tiles = (uint64_t)((N + 32 * nt - 1) / (32 * nt)) * nbatch;
     const uint64_t waves = (tiles + kSMs - 1) / kSMs;
-    const double cost = (double)waves * nt;
+    const double eff = nt >= 4 ? 1.0 : (nt == 3 ? 0.9 : 0.8);
+    const double cost = (double)waves * nt / eff;
     if (best == 0 || cost <= best_cost) { best = nt; best_cost = cost; }
   }
   return best;
@@ -480,13 +485,19 @@ static int dht_launch(const double* A, uint32_t lda, const double* const* Bv, in
   }
   // results of <= 64 rows (kr-sharded forward / grad / rot contractions at 8 ranks): 64-row
   // tiles.  Measured with the 8 shards of cfg3 on one B200 (profiles/r1h_tile64_timing.txt):
-  // batched launches 19 % faster, single right-hand sides 5-25 % slower (too few tiles), so
-  // the default takes them for >= 3 right-hand sides; CHB_DHT_TILE64=0 / 1: never / always.
+  // batched launches 19 % faster; single right-hand sides were 5-25 % slower with the
+  // 128-256 column tiles of round 1 (too few tiles) -- with the 64 / 96 column tiles they
+  // fill the SMs as well, so 64-row tiles now serve every result of <= 64 rows.
+  // CHB_DHT_TILE64=0: never; =2: the round-1 rule (>= 3 right-hand sides, nt >= 4).
   static const int tile64 = [] { const char* e = getenv("CHB_DHT_TILE64");
-                                 return e ? (e[0] == '1' ? 1 : 0) : 2; }();
+                                 return e ? atoi(e) : 1; }();
   if (wide && M <= 64 && (tile64 == 1 || (tile64 == 2 && nbatch >= 3))) {
     cudaError_t e;
-    switch (pick_wide64_nt(p.N, nbatch)) {
+    int nt64 = pick_wide64_nt(p.N, nbatch);
+    if (tile64 == 2 && nt64 < 4) nt64 = 4;
+    switch (nt64) {
+      case 2: e = launch_wide<2, 4>(p, nbatch, (cudaStream_t)stream); break;
+      case 3: e = launch_wide<3, 4>(p, nbatch, (cudaStream_t)stream); break;
       case 4: e = launch_wide<4, 4>(p, nbatch, (cudaStream_t)stream); break;
       case 5: e = launch_wide<5, 4>(p, nbatch, (cudaStream_t)stream); break;
       case 6: e = launch_wide<6, 4>(p, nbatch, (cudaStream_t)stream); break;
