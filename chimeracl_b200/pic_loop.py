@@ -37,6 +37,8 @@ class PIC_loop:
         # particles of the trash bin, as it does in the reference.
         self.align_every = int(align_every) if align_every else 0
         self.use_cuda_graph = bool(use_cuda_graph)
+        import os
+        self.early_rho_gather = os.environ.get('CHB_EARLY_RHO_GATHER', '1') != '0'
         self._graph = None
         self._graph_pool = None
         self._graph_stream = None
@@ -309,13 +311,27 @@ class PIC_loop:
         E and B grids."""
         S = solver.shards
         self.timer_start()
-        for _ in S():
-            solver.fb_transform(vects=['J', ], dir=0, smooth=True)
-        if charge_ready is not None:
-            charge_ready()
-        for _ in S():
-            solver.fb_transform(scals=['rho', ], dir=0, smooth=True)
-        rho_ready = solver.gather_spectral(['rho'])
+        if getattr(self, 'early_rho_gather', True):
+            # one component of J first (the sum of rho over the ranks is still in flight),
+            # then rho, whose all-gather then runs under the other two components of J
+            comps = ['J' + c for c in solver.Args['vec_comps']]
+            for _ in S():
+                solver.fb_transform(scals=comps[:1], dir=0, smooth=True)
+            if charge_ready is not None:
+                charge_ready()
+            for _ in S():
+                solver.fb_transform(scals=['rho', ], dir=0, smooth=True)
+            rho_ready = solver.gather_spectral(['rho'])
+            for _ in S():
+                solver.fb_transform(scals=comps[1:], dir=0, smooth=True)
+        else:
+            for _ in S():
+                solver.fb_transform(vects=['J', ], dir=0, smooth=True)
+            if charge_ready is not None:
+                charge_ready()
+            for _ in S():
+                solver.fb_transform(scals=['rho', ], dir=0, smooth=True)
+            rho_ready = solver.gather_spectral(['rho'])
         self.timer_record('transform')
 
         self.timer_start()

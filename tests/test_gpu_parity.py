@@ -1034,3 +1034,28 @@ def test_cuda_graph_with_moving_window(comm):
     # momenta of near-axis particles amplify the rounding noise of the m = 1 fields (1/r)
     for k in ("px", "py", "pz", "g_inv"):
         assert rel_err(e1.DataDev[k].get(), e0.DataDev[k].get()) < 1e-6, k
+
+
+# ----------------------------------------------------------------------------- periodic align
+def test_align_every_matches_oracle(comm):
+    """PIC_loop(align_every=2): the loop calls sort_parts + align_parts itself at steps 2 and
+    4; the oracle gets the same calls at the same places.  Integer products bit-exact,
+    fields / momenta to the full-step tolerance 1e-10."""
+    from chimeracl_b200.pic_loop import PIC_loop
+    G = load_golden(1)
+    S, P, I = gpu_case_from_golden(G, comm)
+    loop = PIC_loop(solvers=[S], species=[P, I], align_every=2)
+    So, Po, Io = oracle_case_from_golden(G, NumpyKernels(1))
+    for it in range(5):
+        loop.step()
+        if it > 0 and it % 2 == 0:
+            Po.sort_parts(So)
+            Po.align_parts()
+        O.pic_step(So, [Po, Io])
+    comm.synchronize()
+    assert int(P.Args["Np"]) == Po.Args["Np"]
+    assert np.array_equal(P.DataDev["sort_indx"].get(), Po.D["sort_indx"])
+    for k in ("Ex_m0", "Ez_m1", "Bz_m1", "rho_m0", "Jx_m1"):
+        assert rel_err(S.DataDev[k].get(), So.D[k]) < 1e-10, k
+    for k in ("x", "y", "z", "px", "py", "pz", "g_inv", "w"):
+        assert rel_err(P.DataDev[k].get(), Po.D[k]) < 1e-10, k
