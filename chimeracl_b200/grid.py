@@ -61,8 +61,11 @@ class Grid(GridMethodsCL):
             pg = getattr(self.comm, 'process_group', None)
             work = None
             if pg is not None:
-                from .parallel import allreduce_sum_async
-                work = allreduce_sum_async(self._flat['rho'], pg)
+                peer = getattr(self, 'peer_reduce_flat', None)
+                work = peer('rho') if peer is not None else None
+                if work is None:
+                    from .parallel import allreduce_sum_async
+                    work = allreduce_sum_async(self._flat['rho'], pg)
             self._pending_rho = work if work is not None else True
             return
         self.postproc_depose_scalar('rho')

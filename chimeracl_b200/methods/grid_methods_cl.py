@@ -121,6 +121,10 @@ class GridMethodsCL(GenericMethodsCL):
         flat = getattr(self, '_flat', {}).get('J')
         if pg is None or flat is None:
             return None
+        peer = getattr(self, 'peer_reduce_flat', None)
+        work = peer('J') if peer is not None else None
+        if work is not None:
+            return work
         from ..parallel import allreduce_sum_async
         return allreduce_sum_async(flat, pg)
 

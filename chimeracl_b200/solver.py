@@ -43,6 +43,17 @@ class _Barrier:
         self.handle.barrier(channel=self.channel)
 
 
+class _EventWait:
+    """Work enqueued on the exchange stream; wait() makes the current stream wait for it."""
+
+    def __init__(self, event):
+        self.event = event
+
+    def wait(self):
+        import torch
+        torch.cuda.current_stream().wait_event(self.event)
+
+
 class SpectralSharding:
     """kr-row sharded field solve over the ranks of the Communicator's process group (no
     reference counterpart: the reference is single-device).  Every rank keeps full-size
@@ -82,11 +93,16 @@ class SpectralSharding:
         # barriers of the symmetric-memory handles, instead of NCCL collectives
         import ctypes
         import os
+        # CHB_PEER_EXCHANGE: 0 = NCCL collectives (default), 1 = own kernels with P2P loads /
+        # stores, multimem = own kernels through the NVSwitch multicast address
         peer = os.environ.get('CHB_PEER_EXCHANGE', '0')
         symm = None
         if peer != '0' and not emulate and world > 1:
             import torch.distributed._symmetric_memory as symm
             self._sharding['peer'] = {}
+            # the exchanges run on their own (high-priority) stream, like NCCL's, so that
+            # they overlap the compute the step enqueues before it waits for them
+            self._sharding['peer_stream'] = torch.cuda.Stream(priority=-1)
 
         def register(key, flat):
             hdl = symm.rendezvous(flat, group=pg)
@@ -128,8 +144,50 @@ class SpectralSharding:
                 self.DataDev[key].t.copy_(t)
             if alloc is not None:
                 register(v, self._flat[v])
+        if alloc is not None:
+            # ... and the raw J / rho deposits, whose sum over the ranks then also goes
+            # through the peer-memory kernel instead of NCCL
+            comps = self.Args['vec_comps']
+            for group, names in (('J', ['J' + c for c in comps]), ('rho', ['rho'])):
+                old = {n + '_m' + str(m): self.DataDev[n + '_m' + str(m)].t
+                       for n in names for m in range(self.Args['M'] + 1)}
+                self._flat[group] = self._alloc_group(names, shape, alloc)
+                for key, t in old.items():
+                    self.DataDev[key].t.copy_(t)
+                register(group, self._flat[group])
         self._shard = None if emulate else _Shard(*spectral_rows(K, rank, world)[:2])
         return self
+
+    def _on_exchange_stream(self, fn):
+        """Run fn() on the exchange stream, ordered after everything enqueued so far on the
+        current stream; returns a handle whose wait() orders the current stream after it."""
+        import torch
+        st = self._sharding
+        side = st['peer_stream']
+        ready = torch.cuda.Event()
+        ready.record()
+        with torch.cuda.stream(side):
+            side.wait_event(ready)
+            fn()
+            done = torch.cuda.Event()
+            done.record(side)
+        return _EventWait(done)
+
+    def peer_reduce_flat(self, key):
+        """Sum over the ranks of the flat symmetric buffer `key` ('J', 'rho', 'E', 'B') with
+        chb_peer_allreduce_f64, asynchronously on the exchange stream; None when the
+        peer-memory exchange is off (the caller then uses NCCL)."""
+        st = self.__dict__.get('_sharding')
+        if st is None or 'peer' not in st or key not in st['peer']:
+            return None
+        hdl, ptrs, mc = st['peer'][key]
+        n = self._flat[key].numel()
+
+        def run():
+            hdl.barrier(channel=0)             # every rank's partial sums are written
+            self._call('chb_peer_allreduce_f64', ptrs, st['world'], st['rank'], mc, n)
+            hdl.barrier(channel=1)             # every block's totals are stored
+        return self._on_exchange_stream(run)
 
     def spectral_sharding_enabled(self):
         return self.__dict__.get('_sharding') is not None
@@ -158,22 +216,23 @@ class SpectralSharding:
             return _Done()
         keys = [n + '_fb_m' + str(m) for n in names for m in range(self.Args['M'] + 1)]
         if 'peer' in st:
-            # push the owned rows into every rank's array; the barrier that makes all ranks'
-            # rows visible is only enqueued by .wait(), so the work issued in between runs
-            # ahead of it
+            # push the owned rows into every rank's array (P2P stores or one multimem.st),
+            # on the exchange stream, between two cross-rank barriers: the first orders the
+            # push after every rank's last use of the previous contents (write-after-read;
+            # also for direct callers such as Diagnostics), the second makes all ranks'
+            # rows visible
             chunk = st['R'] * int(self.Args['Nx']) * 2
             own = (self._shard.hi - self._shard.lo) * int(self.Args['Nx']) * 2
-            # write-after-read: no rank may still be contracting with the previous contents
-            # of these arrays when the new rows land in them.  Inside PIC_loop the barriers
-            # of the previous reduce_grid_fields() already order that, a direct caller
-            # (Diagnostics, restore_B_fb(gathered=False)) has no such guarantee: one cheap
-            # cross-rank barrier before the push makes it unconditional
-            st['peer'][keys[0]][0].barrier(channel=2)
-            for key in keys:
-                _, ptrs, mc = st['peer'][key]
-                self._call('chb_peer_allgather_f64', ptrs, st['world'], st['rank'], mc,
-                           st['rank'] * chunk, own)
-            return _Barrier(st['peer'][keys[0]][0])
+            hdl0 = st['peer'][keys[0]][0]
+
+            def run():
+                hdl0.barrier(channel=2)
+                for key in keys:
+                    _, ptrs, mc = st['peer'][key]
+                    self._call('chb_peer_allgather_f64', ptrs, st['world'], st['rank'], mc,
+                               st['rank'] * chunk, own)
+                hdl0.barrier(channel=0)
+            return self._on_exchange_stream(run)
         from .parallel import allgather_rows_async
         stores = [st['stores'][k] for k in keys]
         return allgather_rows_async(stores, st['rank'], self.comm.process_group) or _Done()
@@ -186,13 +245,9 @@ class SpectralSharding:
         if st is None or st['emulate'] or st['world'] == 1:
             return _Done()
         if 'peer' in st:
-            for v in vects:
-                hdl, ptrs, mc = st['peer'][v]
-                hdl.barrier(channel=0)             # every rank's partial sums are written
-                self._call('chb_peer_allreduce_f64', ptrs, st['world'], st['rank'], mc,
-                           self._flat[v].numel())
-                hdl.barrier(channel=1)             # every block's totals are stored
-            return _Done()
+            works = [self.peer_reduce_flat(v) for v in vects]
+            from .parallel import _Works
+            return _Works(works)
         from .parallel import allreduce_each_async
         return allreduce_each_async([self._flat[v] for v in vects],
                                     self.comm.process_group) or _Done()
