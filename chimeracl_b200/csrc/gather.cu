@@ -67,6 +67,9 @@ struct GatherArgs {
   const double* eb[6 * (M + 1)];  // [m][E,B][x,y,z]
   GridGeom geom;
   uint32_t tiles_per_row, ntiles, cells_per_tile;
+  // walk over empty tiles without a pipeline slot (costs a dependent load per tile: only
+  // worth it when most tiles are expected to be empty)
+  uint32_t skip_empty;
 };
 
 // shared-memory layout of ONE pipeline buffer
@@ -81,6 +84,7 @@ struct GatBuf {
 struct TileDesc {
   uint32_t P0, P1;     // particle range in sorted order
   int ir, ix0, ncell;  // row, first cell column, cells
+  bool valid;          // false: the CTA's tile sequence is exhausted
 };
 
 struct GatherCtx {
@@ -220,18 +224,29 @@ gather_push_kernel(GatherArgs<M> a) {
   cx.Nr_cell = cx.g.Nr - 1;
   const int tid = threadIdx.x;
 
-  auto load_desc = [&](uint32_t t) {
+  // descriptor of the next NON-EMPTY tile of this CTA's stride sequence at or after
+  // `tnext` (a rank of a multi-GPU run holds particles in a fraction of the rows: walking
+  // the empty tiles through the pipeline cost half of the kernel time at 8 ranks);
+  // the loads are CTA-uniform
+  uint32_t tnext = blockIdx.x;
+  const uint32_t dt = gridDim.x;
+  auto load_desc = [&]() {
     TileDesc d;
     d.P0 = d.P1 = 0;
     d.ir = d.ix0 = d.ncell = 0;
-    if (t < a.ntiles) {
+    d.valid = false;
+    while (tnext < a.ntiles) {
+      const uint32_t t = tnext;
+      tnext += dt;
       d.ir = (int)(t / a.tiles_per_row);
       d.ix0 = (int)(t - (uint32_t)d.ir * a.tiles_per_row) * (int)a.cells_per_tile;
       d.ncell = min((int)a.cells_per_tile, cx.Nx_cell - d.ix0);
       const uint32_t c0 = (uint32_t)d.ir * (uint32_t)cx.Nx_cell + (uint32_t)d.ix0;
       d.P0 = __ldg(a.cell_offset + c0);
       d.P1 = __ldg(a.cell_offset + c0 + d.ncell);
+      if (!a.skip_empty || d.P1 > d.P0) { d.valid = true; break; }
     }
+    if (!d.valid) d.P0 = d.P1 = 0;
     return d;
   };
   auto load_sidx = [&](const TileDesc& d, uint32_t* sv) {
@@ -279,24 +294,22 @@ gather_push_kernel(GatherArgs<M> a) {
   };
 
   // ---- pipeline prologue
-  uint32_t t = blockIdx.x;
-  const uint32_t dt = gridDim.x;
-  TileDesc d0 = load_desc(t);
+  TileDesc d0 = load_desc();
   uint32_t sv0[kGatSlots], sv1[kGatSlots];
   load_sidx(d0, sv0);
   issue(d0, sv0, bufs[0]);
-  TileDesc d1 = load_desc(t + dt);
+  TileDesc d1 = load_desc();
   load_sidx(d1, sv1);
-  TileDesc d2 = load_desc(t + 2 * dt);
+  TileDesc d2 = load_desc();
   int cur = 0;
 
-  for (; t < a.ntiles; t += dt) {
-    cp_async_wait_all();     // this thread's copies for tile t have landed
-    __syncthreads();         // everybody's have; tile t-dt fully consumed
-    issue(d1, sv1, bufs[cur ^ 1]);                 // stage C for tile t+dt
+  while (d0.valid) {
+    cp_async_wait_all();     // this thread's copies for tile d0 have landed
+    __syncthreads();         // everybody's have; the previous tile is fully consumed
+    issue(d1, sv1, bufs[cur ^ 1]);                 // stage C for the next tile
     uint32_t sv2[kGatSlots];
-    load_sidx(d2, sv2);                            // stage B for tile t+2dt
-    const TileDesc d3 = load_desc(t + 3 * dt);     // stage A for tile t+3dt
+    load_sidx(d2, sv2);                            // stage B for the one after
+    const TileDesc d3 = load_desc();               // stage A
 
     // ---- stage D: tile t
     const GatBuf<M>& B = bufs[cur];
@@ -332,12 +345,16 @@ static int launch_gather(const double* x, const double* y, const double* z, doub
                          const uint32_t* np_stay, GridGeom g, uint32_t np,
                          const double* const* eb, cudaStream_t st) {
   GatherArgs<M> a{x, y, z, px, py, pz, g_inv, sort_indx, cell_offset, factor_push, np_stay,
-                  {}, g, 0, 0, 0};
+                  {}, g, 0, 0, 0, 0};
   for (int k = 0; k < 6 * (M + 1); ++k) a.eb[k] = eb[k];
   // tile width from the mean filling, so that a tile's particles fit one pipelined round
   const double ncells = (double)(g.Nx - 1) * (double)(g.Nr - 1);
   const double ppc = ncells > 0 ? (double)np / ncells : 1.0;
   uint32_t cpt = (uint32_t)(CHB_GAT_FILL * kGatRound / (ppc > 1e-9 ? ppc : 1e-9));
+  // mean filling far below what one tile holds although the tile is as wide as it gets:
+  // the particles sit in a fraction of the grid (a rank's band of a multi-GPU run, an LWFA
+  // slab) -- most tiles are empty
+  a.skip_empty = ppc < 0.5 * kGatRound / kGatCells ? 1u : 0u;
   if (cpt > (uint32_t)kGatCells) cpt = kGatCells;
   if (cpt < 4) cpt = 4;
   a.cells_per_tile = cpt;

@@ -17,6 +17,7 @@
 //
 // STATUS: opt-in (CHB_PEER_EXCHANGE=1 / multimem).  Run on 2 and 8 B200 in round 2 (parity
 // 1.5e-14 / 8.4e-14 against the replicated solve); NCCL stays the default, see DESIGN.md 5.
+#include <cstdlib>
 #include "common.cuh"
 #include "../../include/chimera_b200.h"
 
@@ -49,10 +50,10 @@ peer_allreduce_kernel(const __grid_constant__ PeerBufs bufs, int world, size_t b
 }
 
 // (multimem.ld_reduce / .st take no vector form for .f64 on sm_100a -- ptxas rejects .v2.f64 --
-// so every thread keeps eight independent 8-byte reductions in flight instead)
+// so every thread keeps sixteen independent 8-byte reductions in flight instead)
 __global__ void __launch_bounds__(512)
 multimem_allreduce_kernel(double* mc, size_t begin, size_t end) {
-  constexpr int U = 8;
+  constexpr int U = 16;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i0 = begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < end;
        i0 += stride * U) {
@@ -93,10 +94,19 @@ peer_push_kernel(const __grid_constant__ PeerBufs bufs, int world, int rank, siz
 // ... or stores it once through the multicast address (the switch fans it out)
 __global__ void __launch_bounds__(512)
 multimem_push_kernel(const double* __restrict__ src, double* mc, size_t begin, size_t end) {
+  constexpr int U = 8;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < end; i += stride) {
-    const double v = src[i];
-    asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(mc + i), "d"(v) : "memory");
+  for (size_t i0 = begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < end;
+       i0 += stride * U) {
+    double v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (i0 + u * stride < end) v[u] = src[i0 + u * stride];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (i0 + u * stride < end)
+        asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(mc + i0 + u * stride),
+                     "d"(v[u]) : "memory");
   }
 }
 
@@ -104,13 +114,25 @@ multimem_push_kernel(const double* __restrict__ src, double* mc, size_t begin, s
 
 using namespace chb;
 
+// CTAs of the exchange kernels.  They run on their own stream next to the step's compute
+// kernels: a grid that fills the GPU (the first version: 4 x 148 CTAs) is no faster -- the
+// NVLink ports, not the SMs, bound it -- and starves the compute kernels it is meant to
+// overlap (8-GPU timeline, profiles/r2_trace_8gpu_multimem_v2.txt: a 24 us contraction
+// took 347 us next to it).  CHB_PEER_CTAS overrides.
+static int peer_ctas() {
+  static const int n = [] { const char* e = getenv("CHB_PEER_CTAS");
+                            const int v = e ? atoi(e) : 32;
+                            return v < 1 ? 1 : (v > 8 * kSMs ? 8 * kSMs : v); }();
+  return n;
+}
+
 extern "C" int chb_peer_allgather_f64(const uint64_t* peer_ptrs_host, int world, int rank,
                                       uint64_t multicast_ptr, size_t begin, size_t count,
                                       void* stream) {
   if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world || !peer_ptrs_host)
     return CHB_ERR_ARG;
   if (count == 0 || world == 1) return CHB_OK;
-  const int grid = 2 * kSMs;
+  const int grid = peer_ctas();
   if (multicast_ptr) {
     multimem_push_kernel<<<grid, 512, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const double*>(peer_ptrs_host[rank]),
@@ -137,7 +159,7 @@ extern "C" int chb_peer_allreduce_f64(const uint64_t* peer_ptrs_host, int world,
   const size_t begin = per * rank;
   const size_t end = rank == world - 1 ? n : begin + per;
   if (end <= begin) return CHB_OK;
-  const int grid = 4 * kSMs;
+  const int grid = peer_ctas();
   if (multicast_ptr) {
     multimem_allreduce_kernel<<<grid, 512, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<double*>(multicast_ptr), begin, end);
