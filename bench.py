@@ -646,6 +646,11 @@ def run_ours(args):
             "config": bench_config(A, np_all if scaling == "strong" else np_gpu, world, scaling),
             "field_solve": ("kr rows sharded x%d (all-gather rho/G spectra, all-reduce E/B "
                             "partials)" % world) if shard_solve else "replicated",
+            "exchange": (("own kernels over NVLink peer memory (chb_peer_*: %s), exchange stream"
+                          % ("NVSwitch multimem" if any(v[2] for v in solver._sharding["peer"].values())
+                             else "P2P loads/stores"))
+                         if shard_solve and "peer" in solver._sharding else
+                         ("NCCL" if world > 1 else None)),
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e_value, "unit": "particle-steps/s",
                     "h2d_bytes_per_step": bytes_io[0], "d2h_bytes_per_step": bytes_io[1],

@@ -93,9 +93,24 @@ class SpectralSharding:
         # barriers of the symmetric-memory handles, instead of NCCL collectives
         import ctypes
         import os
-        # CHB_PEER_EXCHANGE: 0 = NCCL collectives (default), 1 = own kernels with P2P loads /
-        # stores, multimem = own kernels through the NVSwitch multicast address
-        peer = os.environ.get('CHB_PEER_EXCHANGE', '0')
+        # CHB_PEER_EXCHANGE: 0 = NCCL collectives, 1 = own kernels with P2P loads / stores,
+        # multimem = own kernels through the NVSwitch multicast address, auto (default)
+        peer = os.environ.get('CHB_PEER_EXCHANGE', 'auto')
+        if peer == 'auto':
+            # measured (profiles/README.md, round 2): through the NVSwitch multicast address
+            # the six exchanges of a step take 1.5 ms instead of NCCL's 2.3 ms (f64 sums run
+            # NCCL's RING_LL protocol, not NVLS) on 8 GPUs, 2.87 against 3.16 ms per step;
+            # on 2 GPUs NCCL is as fast.  Only used where a probe allocation shows that
+            # symmetric memory with a multicast address is available; anything else: NCCL.
+            peer = '0'
+            if world >= 8 and not emulate and pg is not None:
+                try:
+                    import torch.distributed._symmetric_memory as _symm
+                    probe = _symm.empty(1024, dtype=torch.float64, device=self.comm.device)
+                    if int(getattr(_symm.rendezvous(probe, group=pg), 'multicast_ptr', 0) or 0):
+                        peer = 'multimem'
+                except Exception:
+                    peer = '0'
         symm = None
         if peer != '0' and not emulate and world > 1:
             import torch.distributed._symmetric_memory as symm

@@ -14,7 +14,7 @@ has parity && timeout 300 $TR --master-port 29516 tools/sharded_parity.py 2>&1 |
 # 2. bench: replicated, sharded, sharded with the collectives on a high-priority stream
 #    (the contraction kernel holds whole SMs, NCCL only gets them between waves)
 bench() {  # tag, env, extra flags
-  env $2 timeout 300 $TR --master-port 29517 bench.py --gpus $N --steps 10 --warmup 3 --no-cpu-baseline $3 \
+  env $2 timeout 300 $TR --master-port 29517 bench.py --gpus $N --steps 10 --warmup 3 --no-cpu-baseline $BENCH_FLAGS $3 \
     > gpurun_out/bench_${N}gpu_$1.json 2> gpurun_out/bench_${N}gpu_$1.err
   python - "$1" <<PY
 import json, sys
