@@ -170,3 +170,37 @@ def test_injected_slab_is_dealt_to_ranks_by_radial_bands():
     assert np.array_equal(x[i0], xs[i1])
     assert np.allclose(r[i0], rs[i1], rtol=1e-13, atol=1e-15)
     assert np.allclose(w[i0], ws[i1], rtol=1e-13, atol=0)
+
+
+def test_argsdict_never_leaks_pending_values():
+    """Args['Np_stay'] is produced lazily (asynchronous read-back); every read path of the
+    dict -- items(), values(), copy(), dict(), ** -- must hand out the number."""
+    from chimeracl_b200.methods.generic_methods_cl import ArgsDict
+    calls = []
+
+    def make(v):
+        def fn():
+            calls.append(v)
+            return v
+        return fn
+    a = ArgsDict({"Np": 10})
+    a.set_lazy("Np_stay", make(7))
+    assert dict(a) == {"Np": 10, "Np_stay": 7}
+    a.set_lazy("Np_stay", make(8))
+    assert sorted(a.items()) == [("Np", 10), ("Np_stay", 8)]
+    a.set_lazy("Np_stay", make(9))
+    assert 9 in list(a.values())
+    a.set_lazy("Np_stay", make(11))
+    assert {**a}["Np_stay"] == 11
+    a.set_lazy("Np_stay", make(12))
+    assert a.copy()["Np_stay"] == 12 and a.pop("Np_stay") == 12
+    assert calls == [7, 8, 9, 11, 12]            # each resolved exactly once
+    assert a.get("missing", 3) == 3
+
+
+def test_contraction_tile_rule_is_exported():
+    """chb_dht_tile_columns (the 128-row tile width rule) loads and answers without a GPU."""
+    from chimeracl_b200 import _lib
+    lib = _lib.load()
+    assert lib.chb_dht_tile_columns(511, 8192, 1) == 112     # 4 x 74 = 296 tiles = 2 waves
+    assert lib.chb_dht_tile_columns(511, 4096, 1) == 112
