@@ -209,7 +209,11 @@ __device__ __forceinline__ void gather_one(const GatherArgs<M>& a, const GatherC
   a.g_inv[s] = g_p_inv;
 }
 
-template <int M>
+// SKIP: tiles without particles are stepped over while fetching descriptors (a dependent
+// load per tile, outside the pipeline) -- for particle sets that occupy a fraction of the
+// grid; !SKIP: every tile takes a pipeline slot (uniform fillings: nothing to skip, and the
+// descriptor fetch stays free of data-dependent control flow)
+template <int M, bool SKIP>
 __global__ void __launch_bounds__(kGatThreads, kGatCtasPerSm)
 gather_push_kernel(GatherArgs<M> a) {
   constexpr int MM = M > 0 ? M : 1;
@@ -235,16 +239,31 @@ gather_push_kernel(GatherArgs<M> a) {
     d.P0 = d.P1 = 0;
     d.ir = d.ix0 = d.ncell = 0;
     d.valid = false;
-    while (tnext < a.ntiles) {
+    if (SKIP) {
+      while (tnext < a.ntiles) {
+        const uint32_t t = tnext;
+        tnext += dt;
+        d.ir = (int)(t / a.tiles_per_row);
+        d.ix0 = (int)(t - (uint32_t)d.ir * a.tiles_per_row) * (int)a.cells_per_tile;
+        d.ncell = min((int)a.cells_per_tile, cx.Nx_cell - d.ix0);
+        const uint32_t c0 = (uint32_t)d.ir * (uint32_t)cx.Nx_cell + (uint32_t)d.ix0;
+        d.P0 = __ldg(a.cell_offset + c0);
+        d.P1 = __ldg(a.cell_offset + c0 + d.ncell);
+        if (d.P1 > d.P0) { d.valid = true; break; }
+      }
+    } else {
+      // every tile takes a pipeline slot: nothing here depends on the loaded offsets
       const uint32_t t = tnext;
       tnext += dt;
-      d.ir = (int)(t / a.tiles_per_row);
-      d.ix0 = (int)(t - (uint32_t)d.ir * a.tiles_per_row) * (int)a.cells_per_tile;
-      d.ncell = min((int)a.cells_per_tile, cx.Nx_cell - d.ix0);
-      const uint32_t c0 = (uint32_t)d.ir * (uint32_t)cx.Nx_cell + (uint32_t)d.ix0;
-      d.P0 = __ldg(a.cell_offset + c0);
-      d.P1 = __ldg(a.cell_offset + c0 + d.ncell);
-      if (!a.skip_empty || d.P1 > d.P0) { d.valid = true; break; }
+      if (t < a.ntiles) {
+        d.valid = true;
+        d.ir = (int)(t / a.tiles_per_row);
+        d.ix0 = (int)(t - (uint32_t)d.ir * a.tiles_per_row) * (int)a.cells_per_tile;
+        d.ncell = min((int)a.cells_per_tile, cx.Nx_cell - d.ix0);
+        const uint32_t c0 = (uint32_t)d.ir * (uint32_t)cx.Nx_cell + (uint32_t)d.ix0;
+        d.P0 = __ldg(a.cell_offset + c0);
+        d.P1 = __ldg(a.cell_offset + c0 + d.ncell);
+      }
     }
     if (!d.valid) d.P0 = d.P1 = 0;
     return d;
@@ -361,12 +380,16 @@ static int launch_gather(const double* x, const double* y, const double* z, doub
   a.tiles_per_row = (g.Nx - 1 + cpt - 1) / cpt;
   a.ntiles = a.tiles_per_row * (g.Nr - 1);
   const int smem = 2 * (int)sizeof(GatBuf<M>);
-  cudaError_t e = cudaFuncSetAttribute(gather_push_kernel<M>,
+  cudaError_t e = cudaFuncSetAttribute(gather_push_kernel<M, false>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(gather_push_kernel<M, true>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return (int)e;
   uint32_t grid = (uint32_t)(kSMs * kGatCtasPerSm);
   if (a.ntiles < grid) grid = a.ntiles;
-  gather_push_kernel<M><<<grid, kGatThreads, smem, st>>>(a);
+  if (a.skip_empty) gather_push_kernel<M, true><<<grid, kGatThreads, smem, st>>>(a);
+  else gather_push_kernel<M, false><<<grid, kGatThreads, smem, st>>>(a);
   CHB_RETURN_LAST_ERROR();
 }
 

@@ -18,7 +18,7 @@ UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 # C-ABI call -> kernels whose per-launch traffic adds up to one call (cfg3, M = 1)
 CALL_KERNELS = {
     "chb_push_depose_push_index": ["depose_kernel<1, 1, 2, 32>"],
-    "chb_gather_push": ["gather_push_kernel<1>"],
+    "chb_gather_push": ["gather_push_kernel<1, 0>"],
     "chb_depose_scalar": ["depose_kernel<1, 0, 0, 128>"],
     "chb_sort_scatter_stable": ["sort_scatter_kernel", "sort_fixup_kernel"],
     "chb_psatd_advance": ["psatd_kernel"],
