@@ -474,6 +474,9 @@ def run_ours(args):
                  "chb_push_depose_push_index": 2 * BYTES["push"] + BYTES["sort"] +
                  BYTES["depose_vector"] + 28,
                  "chb_depose_scalar": BYTES["depose_scalar"], "chb_gather_push": BYTES["gather"]}
+    # compulsory bytes per particle of the fused passes themselves: 8 attributes + sort_indx
+    # read, x y z + cell index written
+    own_bytes = {"chb_push_depose_push_index": 64 + 4 + 24 + 4, "chb_push_depose_vector": 64 + 4 + 24}
     rooflines = {}
     for name, kinfo in kernels.items():
         t = kinfo["ms_per_call"] * 1e-3
@@ -482,6 +485,12 @@ def run_ours(args):
             rooflines[name] = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"],
                                "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None,
                                "peak_source": peak_src}
+            if name in own_bytes:
+                # a fused call is credited above with the bytes of every reference stage it
+                # replaces (can exceed the peak); this is what the fused pass itself must move
+                own = own_bytes[name] * np_gpu / t / 1e9
+                rooflines[name].update(fused_pass_bytes_per_particle=own_bytes[name],
+                                       fused_pass_gbs=own, fused_pass_frac=own / peaks["hbm_gbs"])
     dht_names = [k for k in kernels if k.startswith("chb_dht")]
     if dht_names:
         # FP64 contraction: cuBLAS DGEMM of the same shape, timed here, for comparison
