@@ -91,6 +91,32 @@ def test_host_pic_steps_match_golden(monkeypatch, M):
                 assert rel_err(got, G[k]) < 1e-10, k
 
 
+def test_host_align_every_matches_oracle(monkeypatch):
+    """Host logic of PIC_loop(align_every=2) over the emulated C ABI: the loop's own
+    sort_parts + align_parts calls at steps 2 and 4 against the oracle given the same calls."""
+    from chimeracl_b200.pic_loop import PIC_loop
+    from oracle import orchestration as O
+    from oracle.np_kernels import NumpyKernels
+    from helpers import oracle_case_from_golden
+    emu.patch_cuda_host_calls(monkeypatch)
+    G = load_golden(1)
+    S, P, I = _case(G, emu.EmulatedComm())
+    loop = PIC_loop(solvers=[S], species=[P, I], align_every=2)
+    So, Po, Io = oracle_case_from_golden(G, NumpyKernels(1))
+    for it in range(5):
+        loop.step()
+        if it > 0 and it % 2 == 0:
+            Po.sort_parts(So)
+            Po.align_parts()
+        O.pic_step(So, [Po, Io])
+    assert int(P.Args["Np"]) == Po.Args["Np"] < G["in/P/x"].size     # the trash bin was dropped
+    assert np.array_equal(P.DataDev["sort_indx"].get(), Po.D["sort_indx"])
+    for k in ("Ex_m0", "Bz_m1", "rho_m0", "Jx_m1"):
+        assert rel_err(S.DataDev[k].get(), So.D[k]) < 1e-10, k
+    for k in ("x", "px", "g_inv", "w"):
+        assert rel_err(P.DataDev[k].get(), Po.D[k]) < 1e-10, k
+
+
 # ------------------------------------------------------------------ two ranks over gloo
 def _free_port():
     with socket.socket() as s:
