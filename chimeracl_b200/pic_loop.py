@@ -227,12 +227,23 @@ class PIC_loop:
 
     def _graph_signature(self):
         solver = self.mainsolver
-        sig = [float(solver.Args['Xmin']), int(solver.Args['Nx']), int(solver.Args['Nr'])]
+        sig = [float(solver.Args['Xmin']), int(solver.Args['Nx']), int(solver.Args['Nr']),
+               len(solver.DataDev)]
+        # a sample of the field arrays (replacing DataDev entries between steps is legal in
+        # the reference API; code that swaps others should call invalidate_graph())
+        for key in ('Ex_m0', 'Bx_m0', 'Jx_m0', 'rho_m0', 'Ex_fb_m0', 'Gx_fb_m0'):
+            if key in solver.DataDev:
+                sig.append(solver.DataDev[key].ptr)
         for parts in self.species:
             D = parts.DataDev
             sig += [int(parts.Args['Np'])] + [D[k].ptr for k in ('x', 'w', 'sort_indx', 'cell_offset')
                                               if k in D and D[k] is not None]
         return tuple(sig)
+
+    def invalidate_graph(self):
+        """Drop the captured step (the next eligible step runs eagerly, the one after it
+        re-captures): for callers that replace device arrays the signature does not watch."""
+        self._graph = None
 
     def _dn_swap(self):
         solver = self.mainsolver
