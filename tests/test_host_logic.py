@@ -196,11 +196,3 @@ def test_argsdict_never_leaks_pending_values():
     assert a.copy()["Np_stay"] == 12 and a.pop("Np_stay") == 12
     assert calls == [7, 8, 9, 11, 12]            # each resolved exactly once
     assert a.get("missing", 3) == 3
-
-
-def test_contraction_tile_rule_is_exported():
-    """chb_dht_tile_columns (the 128-row tile width rule) loads and answers without a GPU."""
-    from chimeracl_b200 import _lib
-    lib = _lib.load()
-    assert lib.chb_dht_tile_columns(511, 8192, 1) == 112     # 4 x 74 = 296 tiles = 2 waves
-    assert lib.chb_dht_tile_columns(511, 4096, 1) == 112
