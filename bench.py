@@ -602,7 +602,7 @@ def run_ours(args):
     host_in, host_out = host_api.make_host_buffers(eons, solver)
     host_out2 = {k: torch.empty_like(v).pin_memory() for k, v in host_out.items()}
     bytes_io = [0, 0]
-    pipe = host_api.HostStepPipeline(loop, eons)
+    pipe = host_api.HostStepPipeline(loop, eons, depth=int(os.environ.get("CHB_E2E_DEPTH", "2")))
     outs = (host_out, host_out2)
 
     def e2e_step():
