@@ -33,16 +33,6 @@ class _Done:
         pass
 
 
-class _Barrier:
-    """Cross-rank barrier of a symmetric-memory handle, enqueued on the stream by wait()."""
-
-    def __init__(self, handle, channel=0):
-        self.handle, self.channel = handle, channel
-
-    def wait(self):
-        self.handle.barrier(channel=self.channel)
-
-
 class _EventWait:
     """Work enqueued on the exchange stream; wait() makes the current stream wait for it."""
 
