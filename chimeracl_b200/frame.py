@@ -54,21 +54,27 @@ class Frame():
             specie.free_added()
             specie.sort_parts(grid=grid)
             specie.align_parts()
-            Num_ppc = np.int32(np.prod(specie.Args['Nppc']) + 1)
-            tail = specie.DataDev['x'][-Num_ppc:].get() if specie.Args['Np'] > 0 else np.empty(0)
-            x_max = float(tail.max()) if tail.size else -np.inf
-            # multi-GPU: a rank whose radial band is empty (more ranks than cell rows, or
-            # everything of it left the box) has no particles to look at, and the next slab
-            # must start at the same x on every rank: largest x_max over the ranks
-            pg = getattr(getattr(specie, 'comm', None), 'process_group', None)
-            if pg is not None:
-                import torch
-                import torch.distributed as dist
-                if dist.get_world_size(pg) > 1:
-                    dev = specie.comm.device if dist.get_backend(pg) == 'nccl' else 'cpu'
-                    t = torch.tensor([x_max], dtype=torch.float64, device=dev)
-                    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=pg)
-                    x_max = float(t.item())
-            if np.isfinite(x_max):
-                specie.Args['right_lim'] = x_max + 0.5 * specie.Args['ddx']
-            # else: nothing anywhere -- keep the lattice edge make_new_domain recorded
+            self._update_right_lim(specie)
+
+    @staticmethod
+    def _update_right_lim(specie):
+        """right_lim = largest x of the last Nppc+1 (aligned) particles + ddx/2 (reference
+        frame.py:61-64), made safe and consistent for multi-GPU runs."""
+        Num_ppc = np.int32(np.prod(specie.Args['Nppc']) + 1)
+        tail = specie.DataDev['x'][-Num_ppc:].get() if specie.Args['Np'] > 0 else np.empty(0)
+        x_max = float(tail.max()) if tail.size else -np.inf
+        # multi-GPU: a rank whose radial band is empty (more ranks than cell rows, or
+        # everything of it left the box) has no particles to look at, and the next slab
+        # must start at the same x on every rank: largest x_max over the ranks
+        pg = getattr(getattr(specie, 'comm', None), 'process_group', None)
+        if pg is not None:
+            import torch
+            import torch.distributed as dist
+            if dist.get_world_size(pg) > 1:
+                dev = specie.comm.device if dist.get_backend(pg) == 'nccl' else 'cpu'
+                t = torch.tensor([x_max], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX, group=pg)
+                x_max = float(t.item())
+        if np.isfinite(x_max):
+            specie.Args['right_lim'] = x_max + 0.5 * specie.Args['ddx']
+        # else: nothing anywhere -- keep the lattice edge make_new_domain recorded

@@ -88,3 +88,57 @@ def test_sharded_deposit_allreduce_equals_single_process(tmp_path):
     S.depose_charge([P, I])
     for k in got.files:
         assert rel_err(got[k], S.D[k]) < 1e-13, k
+
+
+# ------------------------------------------------------------------ Frame.right_lim over ranks
+class _StubArr:
+    def __init__(self, a):
+        self.a = a
+
+    def __getitem__(self, sl):
+        return _StubArr(self.a[sl])
+
+    def get(self):
+        return self.a
+
+
+class _StubComm:
+    def __init__(self, pg):
+        self.process_group, self.device = pg, "cpu"
+
+
+class _StubSpecies:
+    def __init__(self, x, pg):
+        self.Args = {"Nppc": (2, 2, 4), "Np": x.size, "ddx": 0.5, "right_lim": 7.0}
+        self.DataDev = {"x": _StubArr(x)}
+        self.comm = _StubComm(pg)
+
+
+def _right_lim_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world))
+    from chimeracl_b200.parallel import init_distributed
+    from chimeracl_b200.frame import Frame
+    pg = init_distributed(backend="gloo")
+    # rank 1 holds no particles (its radial band is empty)
+    x = np.linspace(0.0, 10.0 + rank, 40) if rank != 1 else np.empty(0)
+    sp = _StubSpecies(x, pg)
+    Frame._update_right_lim(sp)
+    # nobody has particles: the previous limit stays
+    empty = _StubSpecies(np.empty(0), pg)
+    Frame._update_right_lim(empty)
+    np.savez(os.path.join(out_dir, "lim%d.npz" % rank), lim=sp.Args["right_lim"],
+             lim_empty=empty.Args["right_lim"])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_right_lim_is_the_same_on_every_rank_even_with_an_empty_band(tmp_path):
+    """a rank whose band holds no particles must not fail on max() of an
+    empty array, and all ranks must continue the injection from the same x."""
+    world = 3
+    mp.spawn(_right_lim_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    got = [np.load(tmp_path / ("lim%d.npz" % r)) for r in range(world)]
+    for g in got:
+        assert abs(float(g["lim"]) - (12.0 + 0.25)) < 1e-12      # max over ranks (rank 2: 12.0) + ddx/2
+        assert float(g["lim_empty"]) == 7.0
